@@ -1,0 +1,163 @@
+/*
+ * spsg_raycast.h -- C ABI of the B200-native SPSG-semantic raycaster (libspsg_raycast.so).
+ *
+ * This is the drop-in boundary for the reference's native extension module `raycast_rgbd_cuda`
+ * (reference: torch/utils/raycast_rgbd/raycast_rgbd_cuda.cpp:155-160).  Plain device pointers, sizes
+ * and a cudaStream_t (as void*): no ATen / torch types.  All tensors are caller-owned, contiguous,
+ * and live on the device that is current for the calling thread; nothing is allocated or retained
+ * by the library.  Every call is asynchronous on `stream` and re-entrant per (device, stream).
+ *
+ * Error convention: 0 == SPSG_OK, otherwise an SPSG_ERR_* code; spsg_last_error() returns a
+ * thread-local message.  (The reference prints and exit(-1)s on CUDA errors,
+ * cutil_inline_runtime.h:284-292; this library never exits the process.)
+ *
+ * Layouts (identical to the reference):
+ *   locs            int64 (N,4) rows (z,y,x,chunk)          sparse_mapping  int32 (B,Dz,Dy,Dx), -1 = absent
+ *   vals_sdf        f32 (N,1)    vals_color f32 (N,3)       vals_normal f32 (N,3)   vals_semantic f32 (N,14)
+ *   view_matrix     f32 (I,4,4) row-major camera->grid      intrinsics  f32 (I,4) = fx,fy,mx,my
+ *   image_color     f32 (I,H,W,3)   image_depth f32 (I,H,W)   image_normal f32 (I,H,W,3)
+ *   image_semantic  f32 (I,H,W,14)                           miss == -inf in every channel
+ *   mapping3dto2d   int32 (R,max_pixels_per_voxel)           mapping3dto2d_num int32 (R),  R >= F*N
+ *   d_color (N,3)   d_depth (N,1)   d_normal (N,3)   d_semantic (N,14)
+ * with I = num_chunks * views_per_chunk images; image i renders chunk i / views_per_chunk
+ * (reference style.py:9-16); views_per_chunk == 1 is exactly the reference.
+ */
+#ifndef SPSG_RAYCAST_H_
+#define SPSG_RAYCAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPSG_API __attribute__((visibility("default")))
+#else
+#define SPSG_API
+#endif
+
+#define SPSG_SEMANTIC_CHANNELS 14 /* float14, raycast_rgbd_cuda_kernel.cu:18-21 */
+#define SPSG_GRAD_CHANNELS 21     /* colour 3 + depth 1 + normal 3 + semantic 14 */
+
+enum {
+    SPSG_OK = 0,
+    SPSG_ERR_INVALID_ARGUMENT = 1,
+    SPSG_ERR_CUDA = 2,
+    SPSG_ERR_WORKSPACE_TOO_SMALL = 3
+};
+
+/* spsg_raycast_params.flags */
+enum {
+    SPSG_FLAG_NO_CLIP = 1u << 0,       /* debug: march every sample like the reference (no ray/box clip)   */
+    SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-brick skipping                                    */
+    SPSG_FLAG_RECORD_HITS = 1u << 2    /* also write the per-pixel hit voxel index into the workspace       */
+};
+
+/* Replaces the reference's `opts` CPU tensor [W,H,depth_min,depth_max,thresh,ray_inc,Dx,Dy,Dz]
+ * (raycast_rgbd.py:24-25, raycast_rgbd_cuda_kernel.cu:443-456) plus the sizes it read off tensors
+ * (:471 max pixels, :490 batch). */
+typedef struct spsg_raycast_params {
+    int32_t width, height;
+    float depth_min, depth_max, thresh_sample_dist, ray_increment;
+    int32_t dimx, dimy, dimz;
+    int32_t num_chunks;           /* B = sparse_mapping.size(0)                        */
+    int32_t views_per_chunk;      /* F >= 1; images = B*F                              */
+    int32_t max_pixels_per_voxel; /* mapping3dto2d.size(1)                             */
+    int64_t num_locs;             /* N = locs.size(0)                                  */
+    uint32_t flags;               /* SPSG_FLAG_*                                       */
+    uint32_t reserved;
+} spsg_raycast_params;
+
+/* Fused 2D losses (reference: depth L1 train.py:635-638, colour L1 loss.py:246-257,
+ * 2D semantic cross-entropy train.py:744-746).  Targets are per image, same pixel layout as the
+ * renderings.  Any target pointer may be NULL to switch that term off. */
+typedef struct spsg_loss_targets {
+    const float *target_depth;    /* (I,H,W) metres; 0 = hole (ignored)                               */
+    const float *target_color;    /* (I,H,W,3) already permuted to channels-last                      */
+    const float *weight_color;    /* (I,H,W) optional per-pixel colour weight or NULL (loss.py:250-253) */
+    const uint8_t *target_label;  /* (I,H,W) class id, 14 = ignore (train.py:614-616)                 */
+    const float *class_weight;    /* (14) cross-entropy class weights (train.py:118-119) or NULL = 1  */
+    float voxelsize;              /* depth scale applied to the rendering (train.py:635)              */
+    float weight_depth, weight_color_loss, weight_semantic; /* loss = sum_k weight_k * loss_k         */
+} spsg_loss_targets;
+
+/* Number of floats in the loss accumulator block written by spsg_raycast_forward_loss. */
+#define SPSG_LOSS_ACCUM_FLOATS 8
+/* acc[0]=sum|d-t| acc[1]=#valid depth  acc[2]=sum|c-t| acc[3]=#valid colour elems
+ * acc[4]=sum w[y]*nll acc[5]=sum w[y]   acc[6]=total weighted loss (after finalize)  acc[7]=reserved */
+
+SPSG_API const char *spsg_version(void);
+SPSG_API const char *spsg_last_error(void);
+
+/* Scratch the forward needs (empty-brick map, optional per-pixel hit records). */
+SPSG_API size_t spsg_workspace_bytes(const spsg_raycast_params *p);
+
+/* == raycast_rgbd_cuda.construct_dense_sparse_mapping (raycast_rgbd_cuda.cpp:93-100,
+ *    raycast_rgbd_cuda_kernel.cu:346-362, 506-533): sparse_mapping := -1, then [chunk,z,y,x] := row. */
+SPSG_API int spsg_build_index(const int64_t *locs, int64_t num_locs, int32_t *sparse_mapping, int32_t num_chunks,
+                              int32_t dimz, int32_t dimy, int32_t dimx, void *stream);
+
+/* == raycast_rgbd_cuda.forward (raycast_rgbd_cuda.cpp:57-91, raycast_rgbd_cuda_kernel.cu:265-297,
+ *    426-503).  sparse_mapping must already hold the index of `locs`.  Differences from the reference,
+ *    none observable through its Python API: mapping3dto2d is not pre-filled with -1 (only entries
+ *    [row][< num[row]] are defined) and only the first F*N counters of mapping3dto2d_num are reset. */
+SPSG_API int spsg_raycast_forward(const spsg_raycast_params *p, const int32_t *sparse_mapping, const int64_t *locs,
+                                  const float *vals_sdf, const float *vals_color, const float *vals_normal,
+                                  const float *vals_semantic, const float *view_matrix, const float *intrinsics,
+                                  float *image_color, float *image_depth, float *image_normal,
+                                  float *image_semantic, int32_t *mapping3dto2d, int32_t *mapping3dto2d_num,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* spsg_build_index + spsg_raycast_forward in one call (what RayCastRGBDFunction.forward does back
+ * to back, raycast_rgbd.py:23-28), sharing one pass over `locs`. */
+SPSG_API int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t *sparse_mapping, const int64_t *locs,
+                                          const float *vals_sdf, const float *vals_color, const float *vals_normal,
+                                          const float *vals_semantic, const float *view_matrix,
+                                          const float *intrinsics, float *image_color, float *image_depth,
+                                          float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
+                                          int32_t *mapping3dto2d_num, void *workspace, size_t workspace_bytes,
+                                          void *stream);
+
+/* == raycast_rgbd_cuda.backward (raycast_rgbd_cuda.cpp:102-140, raycast_rgbd_cuda_kernel.cu:365-423,
+ *    535-586): d_x[v] = sum over views of mean over the first min(num, max_pixels) pixels registered to
+ *    voxel v of grad_x[pixel].  Rows [0, N) of every d_* are fully written (zeros where nothing hit);
+ *    rows >= N are left untouched (the reference zero-fills the whole buffer, Python only ever
+ *    returns [:N], raycast_rgbd.py:42).  Deterministic: no float atomics. */
+SPSG_API int spsg_raycast_backward(const spsg_raycast_params *p, const float *grad_color, const float *grad_depth,
+                                   const float *grad_normal, const float *grad_semantic,
+                                   const int32_t *sparse_mapping, const int32_t *mapping3dto2d,
+                                   const int32_t *mapping3dto2d_num, float *d_color, float *d_depth,
+                                   float *d_normal, float *d_semantic, void *stream);
+
+/* == raycast_rgbd_cuda.raycast_occ (raycast_rgbd_cuda.cpp:142-153, raycast_rgbd_cuda_kernel.cu:300-344,
+ *    589-623).  occ3d u8 (B,1,Dz,Dy,Dx), occ2d u8 (B,1,H,W); uses width,height,depth_min,depth_max,
+ *    ray_increment,dim*,num_chunks of `p`. */
+SPSG_API int spsg_raycast_occ(const spsg_raycast_params *p, const uint8_t *occ3d, uint8_t *occ2d,
+                              const float *view_matrix, const float *intrinsics, void *stream);
+
+/* Fused forward + 2D losses: renders like spsg_raycast_forward_indexed and accumulates the three
+ * loss terms of `t` into loss_accum (SPSG_LOSS_ACCUM_FLOATS floats, zeroed by the call). */
+SPSG_API int spsg_raycast_forward_loss(const spsg_raycast_params *p, int32_t *sparse_mapping, const int64_t *locs,
+                                       const float *vals_sdf, const float *vals_color, const float *vals_normal,
+                                       const float *vals_semantic, const float *view_matrix,
+                                       const float *intrinsics, float *image_color, float *image_depth,
+                                       float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
+                                       int32_t *mapping3dto2d_num, const spsg_loss_targets *t, float *loss_accum,
+                                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused backward of the 2D losses through the raycast: the upstream gradient images are never
+ * materialised; each registered pixel's gradient is recomputed from (rendering, target, loss_accum).
+ * grad_scale multiplies everything (d total / d weighted-loss, normally 1). */
+SPSG_API int spsg_raycast_backward_loss(const spsg_raycast_params *p, const float *image_color,
+                                        const float *image_depth, const float *image_semantic,
+                                        const spsg_loss_targets *t, const float *loss_accum, float grad_scale,
+                                        const int32_t *sparse_mapping, const int32_t *mapping3dto2d,
+                                        const int32_t *mapping3dto2d_num, float *d_color, float *d_depth,
+                                        float *d_normal, float *d_semantic, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPSG_RAYCAST_H_ */
