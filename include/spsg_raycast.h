@@ -51,7 +51,7 @@ enum {
 /* spsg_raycast_params.flags */
 enum {
     SPSG_FLAG_NO_CLIP = 1u << 0,       /* debug: march every sample like the reference (no ray/box clip)   */
-    SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-brick skipping                                    */
+    SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-block skipping                                    */
     SPSG_FLAG_RECORD_HITS = 1u << 2    /* also write the per-pixel hit voxel index into the workspace       */
 };
 
@@ -83,15 +83,17 @@ typedef struct spsg_loss_targets {
     float weight_depth, weight_color_loss, weight_semantic; /* loss = sum_k weight_k * loss_k         */
 } spsg_loss_targets;
 
-/* Number of floats in the loss accumulator block written by spsg_raycast_forward_loss. */
-#define SPSG_LOSS_ACCUM_FLOATS 8
-/* acc[0]=sum|d-t| acc[1]=#valid depth  acc[2]=sum|c-t| acc[3]=#valid colour elems
- * acc[4]=sum w[y]*nll acc[5]=sum w[y]   acc[6]=total weighted loss (after finalize)  acc[7]=reserved */
+/* Number of floats in the loss block written by spsg_raycast_forward_loss:
+ * out[0]=depth L1  out[1]=colour L1  out[2]=semantic CE  out[3]=weight_depth*out[0]+weight_color_loss*out[1]+
+ * weight_semantic*out[2]   out[4]=#valid depth pixels  out[5]=#valid colour elements  out[6]=sum of w[label]
+ * (the normalisers spsg_raycast_backward_loss needs)  out[7]=reserved.  An empty valid set gives NaN, like torch. */
+#define SPSG_LOSS_OUT_FLOATS 8
 
 SPSG_API const char *spsg_version(void);
 SPSG_API const char *spsg_last_error(void);
 
-/* Scratch the forward needs (empty-brick map, optional per-pixel hit records). */
+/* Scratch shared by forward and backward of one call pair: dense SDF brick (4*B*Dz*Dy*Dx bytes), skip-level map,
+ * hit-voxel list, loss accumulators, optional per-pixel hit records.  Must be 256-byte aligned. */
 SPSG_API size_t spsg_workspace_bytes(const spsg_raycast_params *p);
 
 /* == raycast_rgbd_cuda.construct_dense_sparse_mapping (raycast_rgbd_cuda.cpp:93-100,
@@ -129,7 +131,8 @@ SPSG_API int spsg_raycast_backward(const spsg_raycast_params *p, const float *gr
                                    const float *grad_normal, const float *grad_semantic,
                                    const int32_t *sparse_mapping, const int32_t *mapping3dto2d,
                                    const int32_t *mapping3dto2d_num, float *d_color, float *d_depth,
-                                   float *d_normal, float *d_semantic, void *stream);
+                                   float *d_normal, float *d_semantic, void *workspace, size_t workspace_bytes,
+                                   void *stream);
 
 /* == raycast_rgbd_cuda.raycast_occ (raycast_rgbd_cuda.cpp:142-153, raycast_rgbd_cuda_kernel.cu:300-344,
  *    589-623).  occ3d u8 (B,1,Dz,Dy,Dx), occ2d u8 (B,1,H,W); uses width,height,depth_min,depth_max,
@@ -137,25 +140,26 @@ SPSG_API int spsg_raycast_backward(const spsg_raycast_params *p, const float *gr
 SPSG_API int spsg_raycast_occ(const spsg_raycast_params *p, const uint8_t *occ3d, uint8_t *occ2d,
                               const float *view_matrix, const float *intrinsics, void *stream);
 
-/* Fused forward + 2D losses: renders like spsg_raycast_forward_indexed and accumulates the three
- * loss terms of `t` into loss_accum (SPSG_LOSS_ACCUM_FLOATS floats, zeroed by the call). */
+/* Fused forward + 2D losses: renders like spsg_raycast_forward_indexed and writes the three loss terms of `t`,
+ * their weighted total and their normalisers into loss_out (SPSG_LOSS_OUT_FLOATS device floats). */
 SPSG_API int spsg_raycast_forward_loss(const spsg_raycast_params *p, int32_t *sparse_mapping, const int64_t *locs,
                                        const float *vals_sdf, const float *vals_color, const float *vals_normal,
                                        const float *vals_semantic, const float *view_matrix,
                                        const float *intrinsics, float *image_color, float *image_depth,
                                        float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
-                                       int32_t *mapping3dto2d_num, const spsg_loss_targets *t, float *loss_accum,
+                                       int32_t *mapping3dto2d_num, const spsg_loss_targets *t, float *loss_out,
                                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* Fused backward of the 2D losses through the raycast: the upstream gradient images are never
- * materialised; each registered pixel's gradient is recomputed from (rendering, target, loss_accum).
- * grad_scale multiplies everything (d total / d weighted-loss, normally 1). */
+ * materialised; each registered pixel's gradient is recomputed from (rendering, target, loss_out).
+ * grad_scale: device scalar multiplying everything (d objective / d out[3]); NULL means 1. */
 SPSG_API int spsg_raycast_backward_loss(const spsg_raycast_params *p, const float *image_color,
                                         const float *image_depth, const float *image_semantic,
-                                        const spsg_loss_targets *t, const float *loss_accum, float grad_scale,
+                                        const spsg_loss_targets *t, const float *loss_out, const float *grad_scale,
                                         const int32_t *sparse_mapping, const int32_t *mapping3dto2d,
                                         const int32_t *mapping3dto2d_num, float *d_color, float *d_depth,
-                                        float *d_normal, float *d_semantic, void *stream);
+                                        float *d_normal, float *d_semantic, void *workspace, size_t workspace_bytes,
+                                        void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SPSG_RAYCAST_LIB", os.path.join(_HERE, "lib", "libsps
 SPSG_FLAG_NO_CLIP = 1 << 0
 SPSG_FLAG_NO_BRICK_SKIP = 1 << 1
 SPSG_FLAG_RECORD_HITS = 1 << 2
-SPSG_LOSS_ACCUM_FLOATS = 8
+SPSG_LOSS_OUT_FLOATS = 8
 
 # every symbol include/spsg_raycast.h declares (tests check the library exports them all)
 EXPORTS = (
@@ -70,13 +70,13 @@ def _load():
     lib.spsg_raycast_forward_indexed.restype = ctypes.c_int
     lib.spsg_raycast_forward_indexed.argtypes = fwd
     lib.spsg_raycast_backward.restype = ctypes.c_int
-    lib.spsg_raycast_backward.argtypes = [pp] + [vp] * 11 + [vp]
+    lib.spsg_raycast_backward.argtypes = [pp] + [vp] * 11 + [vp, sz, vp]
     lib.spsg_raycast_occ.restype = ctypes.c_int
     lib.spsg_raycast_occ.argtypes = [pp, vp, vp, vp, vp, vp]
     lib.spsg_raycast_forward_loss.restype = ctypes.c_int
     lib.spsg_raycast_forward_loss.argtypes = [pp] + [vp] * 14 + [lt, vp, vp, sz, vp]
     lib.spsg_raycast_backward_loss.restype = ctypes.c_int
-    lib.spsg_raycast_backward_loss.argtypes = [pp, vp, vp, vp, lt, vp, ctypes.c_float] + [vp] * 7 + [vp]
+    lib.spsg_raycast_backward_loss.argtypes = [pp, vp, vp, vp, lt, vp, vp] + [vp] * 7 + [vp, sz, vp]
     return lib
 
 

@@ -7,13 +7,17 @@
 //
 // Design (not a port): see DESIGN.md.  In short
 //   * the march replays the reference's `ray += inc` running sum bit-exactly but jumps over samples
-//     that are provably invalid (outside the grid, or inside an empty 8^3 brick) with a closed form
-//     of the fp32 recurrence that is exact inside one binade;
-//   * the 8 corner indices / SDF values of a sample are fetched as two rounds of independent loads
-//     instead of 16 dependent ones;
-//   * the backward is a deterministic per-voxel gather (no float atomics, no 524288-block launch,
-//     no 164 MB memsets).
+//     that are provably invalid (outside the grid, or inside an empty aligned 4/8/16/32-voxel block)
+//     with a closed form of the fp32 recurrence that is exact inside one binade;
+//   * SDF values are gathered from a dense fp32 brick (NaN = absent voxel) built together with the
+//     index, so one sample costs 8 independent loads instead of 16 dependent ones;
+//   * the march is a converged "while-while" loop (skip phase / sample phase) and the regula-falsi
+//     refinement is deferred until the whole warp has found its crossing, to keep SIMT lanes busy;
+//   * rendered pixels are staged in shared memory and written with coalesced 128-bit stores;
+//   * the backward is a deterministic per-voxel gather over a compacted list of hit voxels (no float
+//     atomics, no 524288-block launch, no 164 MB memsets), optionally fused with the 2D losses.
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -22,9 +26,12 @@
 
 namespace {
 
-constexpr int kBrickLog2 = 3;
-constexpr int kBrick = 1 << kBrickLog2;
+constexpr int kFineLog2 = 2;             // finest skip block: 4^3 voxels
+constexpr int kFine = 1 << kFineLog2;
+constexpr int kSuper = 8;                // hierarchy kernel handles 8^3 fine blocks = 32^3 voxels per CTA
 constexpr float kBoxEps = 1.0f / 64.0f;  // shrink of skip boxes; >> every fp32 error term
+constexpr float kFracGuard = 1.0f / 256.0f;  // fast corner path needs frac(p) in [guard, 1-guard]
+constexpr int kMaxFastDim = 8192;        // fast corner path proven for coordinates < 2^13
 
 thread_local char g_err[512] = "";
 
@@ -44,24 +51,40 @@ int fail_cuda(cudaError_t e, const char *where) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Workspace layout (caller-owned scratch, see spsg_workspace_bytes)
 struct Layout {
-    int nbx, nby, nbz;
-    size_t brick_off, brick_bytes;
-    size_t hits_off, hits_bytes;
+    int n4x, n4y, n4z;  // fine skip blocks per axis
+    size_t dense_off, dense_bytes;  // f32 [B][Dz][Dy][Dx], NaN = absent
+    size_t skip_off, skip_bytes;    // u8  [B][n4z][n4y][n4x] skip level (0 = occupied)
+    size_t list_off, list_bytes;    // backward: int32 counter (256 B) + int2 (voxel, chunk) list
+    size_t loss_off, loss_bytes;    // double[8] loss accumulators
+    size_t hits_off, hits_bytes;    // optional int32 per-pixel hit voxel
     size_t total;
 };
 
 Layout make_layout(const spsg_raycast_params *p) {
     Layout L;
-    L.nbx = (p->dimx + kBrick - 1) >> kBrickLog2;
-    L.nby = (p->dimy + kBrick - 1) >> kBrickLog2;
-    L.nbz = (p->dimz + kBrick - 1) >> kBrickLog2;
+    L.n4x = (p->dimx + kFine - 1) >> kFineLog2;
+    L.n4y = (p->dimy + kFine - 1) >> kFineLog2;
+    L.n4z = (p->dimz + kFine - 1) >> kFineLog2;
     const int F = p->views_per_chunk > 0 ? p->views_per_chunk : 1;
-    L.brick_off = 0;
-    L.brick_bytes = align_up((size_t)p->num_chunks * L.nbx * L.nby * L.nbz, 256);
-    L.hits_off = L.brick_off + L.brick_bytes;
+    size_t off = 0;
+    L.dense_off = off;
+    L.dense_bytes = align_up((size_t)p->num_chunks * p->dimz * p->dimy * p->dimx * sizeof(float), 256);
+    off += L.dense_bytes;
+    L.skip_off = off;
+    L.skip_bytes = align_up((size_t)p->num_chunks * L.n4x * L.n4y * L.n4z, 256);
+    off += L.skip_bytes;
+    L.list_off = off;
+    L.list_bytes = align_up(256 + (size_t)(p->num_locs > 0 ? p->num_locs : 0) * 2 * sizeof(int32_t), 256);
+    off += L.list_bytes;
+    L.loss_off = off;
+    L.loss_bytes = 256;
+    off += L.loss_bytes;
+    L.hits_off = off;
     L.hits_bytes = align_up((size_t)p->num_chunks * F * p->width * p->height * sizeof(int32_t), 256);
-    L.total = L.hits_off + L.hits_bytes;
+    off += L.hits_bytes;
+    L.total = off;
     return L;
 }
 
@@ -76,6 +99,12 @@ __device__ __forceinline__ int round_voxel(float t) {
     return __float2int_rz(__fadd_rn(t, copysignf(0.5f, t)));
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct Ray {
     float camx, camy, camz;
     float dx, dy, dz;
@@ -85,23 +114,22 @@ struct Ray {
 // kernel.cu:287-293 + :72-85 + :194-197, cutil_math.h:1207, cuda_SimpleMatrixUtil.h:888-907.
 __device__ __forceinline__ Ray setup_ray(const float *__restrict__ M, const float *__restrict__ K, unsigned ux,
                                          unsigned uy, float dmin, float dmax) {
-    const float fx = __ldg(K + 0), fy = __ldg(K + 1), mx = __ldg(K + 2), my = __ldg(K + 3);
-    const float xn = __fdiv_rn(__fadd_rn((float)ux, -mx), fx);
-    const float yn = __fdiv_rn(__fadd_rn((float)uy, -my), fy);
+    const float4 k4 = __ldg(reinterpret_cast<const float4 *>(K));  // fx, fy, mx, my
+    const float xn = __fdiv_rn(__fadd_rn((float)ux, -k4.z), k4.x);
+    const float yn = __fdiv_rn(__fadd_rn((float)uy, -k4.w), k4.y);
     const float zc = __fadd_rn(__fadd_rn(dmax, -dmin), dmin);
     const float vx = __fmul_rn(xn, zc), vy = __fmul_rn(yn, zc);
     float r = rsqrtf(__fmaf_rn(zc, zc, __fmaf_rn(vx, vx, __fmul_rn(vy, vy))));
     const float cx = __fmul_rn(vx, r), cy = __fmul_rn(vy, r), cz = __fmul_rn(r, zc);
-    float m[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) m[i] = __ldg(M + i);
+    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(M)), r1 = __ldg(reinterpret_cast<const float4 *>(M) + 1),
+                 r2 = __ldg(reinterpret_cast<const float4 *>(M) + 2);
     Ray o;
-    o.camx = __fadd_rn(m[3], __fmaf_rn(0.0f, m[2], __fmaf_rn(0.0f, m[0], __fmul_rn(0.0f, m[1]))));
-    o.camy = __fadd_rn(m[7], __fmaf_rn(0.0f, m[6], __fmaf_rn(0.0f, m[4], __fmul_rn(0.0f, m[5]))));
-    o.camz = __fadd_rn(m[11], __fmaf_rn(0.0f, m[10], __fmaf_rn(0.0f, m[8], __fmul_rn(0.0f, m[9]))));
-    const float wx = __fmaf_rn(0.0f, m[3], __fmaf_rn(m[2], cz, __fmaf_rn(m[0], cx, __fmul_rn(m[1], cy))));
-    const float wy = __fmaf_rn(0.0f, m[7], __fmaf_rn(m[6], cz, __fmaf_rn(m[4], cx, __fmul_rn(m[5], cy))));
-    const float wz = __fmaf_rn(0.0f, m[11], __fmaf_rn(m[10], cz, __fmaf_rn(m[8], cx, __fmul_rn(m[9], cy))));
+    o.camx = __fadd_rn(r0.w, __fmaf_rn(0.0f, r0.z, __fmaf_rn(0.0f, r0.x, __fmul_rn(0.0f, r0.y))));
+    o.camy = __fadd_rn(r1.w, __fmaf_rn(0.0f, r1.z, __fmaf_rn(0.0f, r1.x, __fmul_rn(0.0f, r1.y))));
+    o.camz = __fadd_rn(r2.w, __fmaf_rn(0.0f, r2.z, __fmaf_rn(0.0f, r2.x, __fmul_rn(0.0f, r2.y))));
+    const float wx = __fmaf_rn(0.0f, r0.w, __fmaf_rn(r0.z, cz, __fmaf_rn(r0.x, cx, __fmul_rn(r0.y, cy))));
+    const float wy = __fmaf_rn(0.0f, r1.w, __fmaf_rn(r1.z, cz, __fmaf_rn(r1.x, cx, __fmul_rn(r1.y, cy))));
+    const float wz = __fmaf_rn(0.0f, r2.w, __fmaf_rn(r2.z, cz, __fmaf_rn(r2.x, cx, __fmul_rn(r2.y, cy))));
     r = rsqrtf(__fmaf_rn(wz, wz, __fmaf_rn(wx, wx, __fmul_rn(wy, wy))));
     o.dx = __fmul_rn(wx, r);
     o.dy = __fmul_rn(wy, r);
@@ -112,39 +140,56 @@ __device__ __forceinline__ Ray setup_ray(const float *__restrict__ M, const floa
     return o;
 }
 
-// Advance the reference's running sum `ray = ray + inc` (kernel.cu:257,260) by `want` >= 1 steps, or by
-// fewer (>= 1) when the closed form would leave the current binade.  Bit-exact: inside [2^e, 2^(e+1))
-// every partial sum is a multiple of u = 2^(e-23), so fl(s + inc) = s + d with d = inc rounded to the
-// u grid -- a constant as long as inc is not an exact tie between two grid points -- and s + j*d is
-// representable, so one fma reproduces j sequential adds.  Anything irregular falls back to real adds.
-__device__ __forceinline__ float advance_ray(float ray, float inc, int want) {
-    if (want > 2) {
-        const float lo = __uint_as_float(__float_as_uint(ray) & 0x7f800000u);  // 2^e <= ray
-        const float u = __fmul_rn(lo, 1.1920928955078125e-07f);                // 2^(e-23)
-        const float d = __fadd_rn(__fadd_rn(lo, inc), -lo);                    // inc on the u grid
-        const float rem = __fadd_rn(inc, -d);                                  // exact remainder
-        const bool regular = (lo >= 1.0f) && (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) &&
-                             (d > 0.0f) && (__fmul_rn(fabsf(rem), 2.0f) != u);
-        if (regular) {
-            // all partial sums must stay below 2^(e+1) - inc so that every add rounds on the u grid
-            const float room = __fadd_rn(__fadd_rn(__fmul_rn(lo, 2.0f), -__fmul_rn(inc, 2.0f)), -ray);
-            const int jmax = (room > 0.0f) ? __float2int_rd(__fdiv_rn(room, d)) : 0;
-            const int j = min(want, jmax);
-            if (j >= 1) return __fmaf_rn((float)j, d, ray);
-        } else {
-            for (int k = 0; k < want; k++) ray = __fadd_rn(ray, inc);
+// The reference's running sum `ray = ray + inc` (kernel.cu:257,260), advanced by many steps at once.
+// Bit-exact: inside a binade [2^e, 2^(e+1)) every partial sum is a multiple of u = 2^(e-23), so
+// fl(s + inc) = s + d with d = inc rounded to the u grid -- a constant as long as inc is not an exact tie
+// between two grid points -- and s + j*d is representable, so one fma reproduces j sequential adds as long
+// as every partial sum stays below 2^(e+1) - inc.  Anything irregular falls back to real adds.
+struct Stepper {
+    float inc, inv_inc;
+    float lo, lim, d, inv_d;  // current binade [lo, 2lo); closed form usable while ray < lim
+    bool regular;
+
+    __device__ __forceinline__ void init(float inc_) {
+        inc = inc_;
+        inv_inc = rcp_approx(inc_);
+        lo = 0.0f; lim = 0.0f; d = inc_; inv_d = inv_inc; regular = false;
+    }
+    __device__ __forceinline__ void rebin(float ray) {
+        lo = __uint_as_float(__float_as_uint(ray) & 0x7f800000u);      // 2^e <= ray
+        const float u = __fmul_rn(lo, 1.1920928955078125e-07f);         // 2^(e-23)
+        d = __fadd_rn(__fadd_rn(lo, inc), -lo);                         // inc on the u grid
+        const float rem = __fadd_rn(inc, -d);                           // exact remainder
+        regular = (lo >= 1.0f) && (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) && (d > 0.0f) &&
+                  (__fmul_rn(fabsf(rem), 2.0f) != u);
+        lim = __fadd_rn(__fmul_rn(lo, 2.0f), -__fmul_rn(inc, 2.0f));   // partial sums must stay below 2lo - inc
+        inv_d = rcp_approx(d);
+    }
+    // advance by `want` >= 1 steps, or by fewer (>= 1) when the closed form would leave the binade
+    __device__ __forceinline__ float advance(float ray, int want) {
+        if (want <= 2) {
+            ray = __fadd_rn(ray, inc);
+            if (want == 2) ray = __fadd_rn(ray, inc);
             return ray;
         }
-        return __fadd_rn(ray, inc);
+        if (!(ray >= lo && ray < __fmul_rn(lo, 2.0f))) rebin(ray);
+        if (regular) {
+            const float room = lim - ray;
+            // floor((lim - ray)/d) computed approximately; the slack inc + d in `lim` dwarfs the error
+            const int jmax = (room > 0.0f) ? __float2int_rd(room * inv_d) : 0;
+            const int j = min(want, jmax);
+            if (j >= 1) return __fmaf_rn((float)j, d, ray);
+            return __fadd_rn(ray, inc);
+        }
+        for (int k = 0; k < want; k++) ray = __fadd_rn(ray, inc);
+        return ray;
     }
-    ray = __fadd_rn(ray, inc);
-    if (want == 2) ray = __fadd_rn(ray, inc);
-    return ray;
-}
+};
 
 struct Volume {
     const int32_t *__restrict__ index;  // this chunk's slice of sparse_mapping
     const float *__restrict__ sdf;      // vals_sdf
+    const float *__restrict__ dense;    // this chunk's slice of the dense SDF brick (NaN = absent)
     int dimx, dimy, dimz;
 };
 
@@ -152,30 +197,9 @@ __device__ __forceinline__ bool in_grid(const Volume &v, int x, int y, int z) {
     return (x | y | z) >= 0 && x < v.dimx && y < v.dimy && z < v.dimz;
 }
 
-// trilinearInterpolationSimpleFastFast (kernel.cu:120-156) without the payload.  Exact corner
-// coordinates, weights, product order and accumulation order of the reference SASS.
-template <bool kNearest>
-__device__ __forceinline__ bool sample_sdf(const Volume &v, float px, float py, float pz, float &dist, int &nearest) {
-    const float qx = __fadd_rn(px, -0.5f), qy = __fadd_rn(py, -0.5f), qz = __fadd_rn(pz, -0.5f);
-    const int x0 = round_voxel(qx), y0 = round_voxel(qy), z0 = round_voxel(qz);
-    const int x1 = round_voxel(__fadd_rn(qx, 1.0f)), y1 = round_voxel(__fadd_rn(qy, 1.0f)),
-              z1 = round_voxel(__fadd_rn(qz, 1.0f));
-    if (kNearest) {
-        const int nx = round_voxel(px), ny = round_voxel(py), nz = round_voxel(pz);
-        nearest = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
-    }
-    if (!(in_grid(v, x0, y0, z0) && in_grid(v, x1, y1, z1))) return false;
-    const int r00 = (z0 * v.dimy + y0) * v.dimx, r10 = (z0 * v.dimy + y1) * v.dimx;
-    const int r01 = (z1 * v.dimy + y0) * v.dimx, r11 = (z1 * v.dimy + y1) * v.dimx;
-    const int i000 = __ldg(v.index + r00 + x0), i100 = __ldg(v.index + r00 + x1);
-    const int i010 = __ldg(v.index + r10 + x0), i110 = __ldg(v.index + r10 + x1);
-    const int i001 = __ldg(v.index + r01 + x0), i101 = __ldg(v.index + r01 + x1);
-    const int i011 = __ldg(v.index + r11 + x0), i111 = __ldg(v.index + r11 + x1);
-    if ((i000 | i100 | i010 | i110 | i001 | i101 | i011 | i111) < 0) return false;
-    const float v000 = __ldg(v.sdf + i000), v100 = __ldg(v.sdf + i100), v010 = __ldg(v.sdf + i010),
-                v001 = __ldg(v.sdf + i001), v110 = __ldg(v.sdf + i110), v011 = __ldg(v.sdf + i011),
-                v101 = __ldg(v.sdf + i101), v111 = __ldg(v.sdf + i111);
-    const float wx = __fadd_rn(px, -floorf(px)), wy = __fadd_rn(py, -floorf(py)), wz = __fadd_rn(pz, -floorf(pz));
+// trilinear weights and accumulation in the reference's exact product / fma order (kernel.cu:132-153).
+__device__ __forceinline__ float trilerp(float wx, float wy, float wz, float v000, float v100, float v010, float v001,
+                                         float v110, float v011, float v101, float v111) {
     const float ax = __fadd_rn(1.0f, -wx), ay = __fadd_rn(1.0f, -wy), az = __fadd_rn(1.0f, -wz);
     const float axay = __fmul_rn(ax, ay), wxay = __fmul_rn(wx, ay), axwy = __fmul_rn(ax, wy), wxwy = __fmul_rn(wx, wy);
     float d = __fmaf_rn(v000, __fmul_rn(axay, az), 0.0f);
@@ -186,22 +210,133 @@ __device__ __forceinline__ bool sample_sdf(const Volume &v, float px, float py, 
     d = __fmaf_rn(v011, __fmul_rn(axwy, wz), d);
     d = __fmaf_rn(v101, __fmul_rn(wxay, wz), d);
     d = __fmaf_rn(v111, __fmul_rn(wxwy, wz), d);
-    dist = d;
+    return d;
+}
+
+// trilinearInterpolationSimpleFastFast (kernel.cu:120-156) without the payload: the exact, fully general
+// evaluation (corner coordinates rounded like the reference, index -> value double gather).
+__device__ __noinline__ bool sample_sdf_exact(const Volume &v, float px, float py, float pz, float &dist) {
+    const float qx = __fadd_rn(px, -0.5f), qy = __fadd_rn(py, -0.5f), qz = __fadd_rn(pz, -0.5f);
+    const int x0 = round_voxel(qx), y0 = round_voxel(qy), z0 = round_voxel(qz);
+    const int x1 = round_voxel(__fadd_rn(qx, 1.0f)), y1 = round_voxel(__fadd_rn(qy, 1.0f)),
+              z1 = round_voxel(__fadd_rn(qz, 1.0f));
+    if (!(in_grid(v, x0, y0, z0) && in_grid(v, x1, y1, z1))) return false;
+    const int r00 = (z0 * v.dimy + y0) * v.dimx, r10 = (z0 * v.dimy + y1) * v.dimx;
+    const int r01 = (z1 * v.dimy + y0) * v.dimx, r11 = (z1 * v.dimy + y1) * v.dimx;
+    const int i000 = __ldg(v.index + r00 + x0), i100 = __ldg(v.index + r00 + x1);
+    const int i010 = __ldg(v.index + r10 + x0), i110 = __ldg(v.index + r10 + x1);
+    const int i001 = __ldg(v.index + r01 + x0), i101 = __ldg(v.index + r01 + x1);
+    const int i011 = __ldg(v.index + r11 + x0), i111 = __ldg(v.index + r11 + x1);
+    if ((i000 | i100 | i010 | i110 | i001 | i101 | i011 | i111) < 0) return false;
+    const float wx = __fadd_rn(px, -floorf(px)), wy = __fadd_rn(py, -floorf(py)), wz = __fadd_rn(pz, -floorf(pz));
+    dist = trilerp(wx, wy, wz, __ldg(v.sdf + i000), __ldg(v.sdf + i100), __ldg(v.sdf + i010), __ldg(v.sdf + i001),
+                   __ldg(v.sdf + i110), __ldg(v.sdf + i011), __ldg(v.sdf + i101), __ldg(v.sdf + i111));
     return true;
 }
 
-// Slab test of the ray against [lo, hi]^3-style box; returns parameter interval.
-__device__ __forceinline__ void slab(float o, float d, float lo, float hi, float &tin, float &tout) {
-    if (d != 0.0f) {
-        const float inv = __frcp_rn(d);
-        const float a = (lo - o) * inv, b = (hi - o) * inv;
-        tin = fmaxf(tin, fminf(a, b));
-        tout = fminf(tout, fmaxf(a, b));
-    } else if (o < lo || o > hi) {
-        tin = __int_as_float(0x7f800000);
-        tout = -__int_as_float(0x7f800000);
+// Same result as sample_sdf_exact.  Fast path: when frac(p) is at least kFracGuard away from 0 and 1 on every
+// axis and 0 <= floor(p), floor(p)+1 < dim, the reference's rounded corner coordinates are exactly floor(p) and
+// floor(p)+1 ("corner coordinates"), and the 8 values come straight from the dense brick where an
+// absent corner is NaN, which the fma chain propagates: valid <=> dist is not NaN.  (A present voxel holding NaN,
+// or inf * 0, makes the reference's sample "valid with NaN distance", which can never satisfy the sign test
+// and leaves the same march state as an invalid sample -- observationally identical.)
+__device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float px, float py, float pz, float &dist) {
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = __fadd_rn(px, -fx), wy = __fadd_rn(py, -fy), wz = __fadd_rn(pz, -fz);
+    const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
+    const float wmin = fminf(wx, fminf(wy, wz)), wmax = fmaxf(wx, fmaxf(wy, wz));
+    const bool fast = fast_ok && wmin >= kFracGuard && wmax <= 1.0f - kFracGuard && (ix | iy | iz) >= 0 &&
+                      ix + 1 < v.dimx && iy + 1 < v.dimy && iz + 1 < v.dimz;
+    if (fast) {
+        const float *__restrict__ b = v.dense + ((size_t)iz * v.dimy + iy) * v.dimx + ix;
+        const int sy = v.dimx, sz = v.dimx * v.dimy;
+        const float v000 = __ldg(b), v100 = __ldg(b + 1), v010 = __ldg(b + sy), v110 = __ldg(b + sy + 1);
+        const float v001 = __ldg(b + sz), v101 = __ldg(b + sz + 1), v011 = __ldg(b + sz + sy),
+                    v111 = __ldg(b + sz + sy + 1);
+        dist = trilerp(wx, wy, wz, v000, v100, v010, v001, v110, v011, v101, v111);
+        return dist == dist;
+    }
+    return sample_sdf_exact(v, px, py, pz, dist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// index + dense brick + skip hierarchy
+// ---------------------------------------------------------------------------------------------
+
+// construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + dense SDF scatter + fine occupancy marks +
+// voxel->pixel counter reset, one pass over locs.
+template <bool kWriteIndex>
+__global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict__ locs, long long n,
+                                                    int32_t *__restrict__ sparse_mapping,
+                                                    const float *__restrict__ vals_sdf, float *__restrict__ dense,
+                                                    uint8_t *__restrict__ skip, int32_t *__restrict__ num, int views,
+                                                    int dimz, int dimy, int dimx, int n4z, int n4y, int n4x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const longlong4 l = locs[i];  // (z, y, x, chunk)
+    const long long z = l.x, y = l.y, x = l.z, b = l.w;
+    const long long cell = ((b * dimz + z) * dimy + y) * dimx + x;
+    if (kWriteIndex) sparse_mapping[cell] = (int32_t)i;
+    if (dense) dense[cell] = __ldg(vals_sdf + i);
+    if (skip) {
+        uint8_t *m = skip + ((b * n4z + (z >> kFineLog2)) * n4y + (y >> kFineLog2)) * n4x + (x >> kFineLog2);
+        if (*reinterpret_cast<volatile uint8_t *>(m) == 0) *m = 1;  // benign race: everybody writes 1
+    }
+    if (num)
+        for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
+}
+
+// Turns the fine occupancy marks (1 = some voxel of this 4^3 block is present) into skip levels, in place:
+//   0 = occupied; k >= 1 = the aligned block of edge 2^(k+1) voxels (4, 8, 16, 32) around it is empty.
+// One CTA per 32^3-voxel super block (8^3 fine blocks).
+__global__ void __launch_bounds__(512) skip_hierarchy_kernel(uint8_t *__restrict__ skip, int n4z, int n4y, int n4x,
+                                                             int sbz, int sby, int sbx) {
+    __shared__ int occ8[64], occ16[8], occ32;
+    const int t = threadIdx.x;
+    if (t < 64) occ8[t] = 0;
+    if (t < 8) occ16[t] = 0;
+    if (t == 0) occ32 = 0;
+    __syncthreads();
+    int sb = blockIdx.x;
+    const int bx = sb % sbx; sb /= sbx;
+    const int by = sb % sby; sb /= sby;
+    const int bz = sb % sbz;
+    const int chunk = sb / sbz;
+    const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
+    const int fx = bx * kSuper + tx, fy = by * kSuper + ty, fz = bz * kSuper + tz;
+    const bool inside = fx < n4x && fy < n4y && fz < n4z;
+    uint8_t *m = skip + (((size_t)chunk * n4z + fz) * n4y + fy) * n4x + fx;
+    const bool occ = inside && (*m != 0);
+    if (occ) {
+        occ8[(tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1)] = 1;
+        occ16[(tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2)] = 1;
+        occ32 = 1;
+    }
+    __syncthreads();
+    if (inside) {
+        uint8_t level = 0;
+        if (!occ) {
+            level = 1;
+            if (!occ8[(tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1)]) {
+                level = 2;
+                if (!occ16[(tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2)]) level = occ32 ? 3 : 4;
+            }
+        }
+        *m = level;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+
+struct LossArgs {
+    const float *target_depth, *target_color, *weight_color;
+    const uint8_t *target_label;
+    const float *class_weight;
+    float voxelsize;
+    double *accum;  // [0]=sum|d-t| [1]=#depth [2]=sum|c-t| [3]=#colour elems [4]=sum w*nll [5]=sum w
+};
 
 struct ForwardArgs {
     const int32_t *sparse_mapping;
@@ -209,211 +344,417 @@ struct ForwardArgs {
     const float *view_matrix, *intrinsics;
     float *image_color, *image_depth, *image_normal, *image_semantic;
     int32_t *mapping3dto2d, *mapping3dto2d_num;
-    const uint8_t *bricks;
+    const float *dense;
+    const uint8_t *skip;
     int32_t *hits;
     int width, height;
     float depth_min, depth_max, thresh, inc;
     int dimx, dimy, dimz;
-    int nbx, nby, nbz;
+    int n4x, n4y, n4z;
     int views, max_pixels;
     long long num_locs;
     unsigned flags;
+    int vec_ok;  // image rows 16-byte aligned: float4 write-out allowed
+    LossArgs loss;
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per CTA: 4 warps of 8x4 pixels
+constexpr int kTilePix = kTileW * kTileH;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Cooperative write-out of one channel group of the CTA tile: smem [kTileH][kTileW*C] -> global rows.
+template <int C>
+__device__ __forceinline__ void store_tile(const float *__restrict__ s, float *__restrict__ g, int img, int x0, int y0,
+                                           int width, int height, bool vec) {
+    const int rows = min(kTileH, height - y0), cols = min(kTileW, width - x0);
+    constexpr int kRow = kTileW * C;
+    if (vec && cols == kTileW) {
+        constexpr int kVecRow = kRow / 4;
+        for (int e = threadIdx.x; e < rows * kVecRow; e += kTilePix) {
+            const int r = e / kVecRow, k = e - r * kVecRow;
+            float4 *dst = reinterpret_cast<float4 *>(g + ((size_t)(img * height + y0 + r) * width + x0) * C) + k;
+            __stcs(dst, reinterpret_cast<const float4 *>(s + r * kRow)[k]);
+        }
+    } else {
+        const int n = cols * C;
+        for (int e = threadIdx.x; e < rows * kRow; e += kTilePix) {
+            const int r = e / kRow, k = e - r * kRow;
+            if (k < n) __stcs(g + ((size_t)(img * height + y0 + r) * width + x0) * C + k, s[r * kRow + k]);
+        }
+    }
+}
 
 // One thread per ray.  kernel.cu:265-297 (init + ray), :190-263 (march), :166-187 (regula falsi),
-// :215-249 (hit write-out + voxel->pixel registration).
-__global__ void __launch_bounds__(kTileW *kTileH) raycast_forward_kernel(const ForwardArgs a) {
+// :215-249 (hit write-out + voxel->pixel registration); kLoss adds the 2D losses (train.py:635-638,
+// loss.py:246-257, train.py:744-746) to the epilogue.
+template <bool kLoss>
+__global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const ForwardArgs a) {
+    __shared__ __align__(16) float s_sem[kTilePix * 14];
+    __shared__ __align__(16) float s_col[kTilePix * 3];
+    __shared__ __align__(16) float s_nrm[kTilePix * 3];
+    __shared__ __align__(16) float s_dep[kTilePix];
+    __shared__ float s_red[4][6];
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned ux = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
-    const unsigned uy = blockIdx.y * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+    const unsigned ux = x0 + tx, uy = y0 + ty;
     const int img = blockIdx.z;
-    if (ux >= (unsigned)a.width || uy >= (unsigned)a.height) return;
+    const bool active = ux < (unsigned)a.width && uy < (unsigned)a.height;
     const int chunk = img / a.views, view = img - chunk * a.views;
     const unsigned pix = uy * a.width + ux;
     const size_t gpix = (size_t)img * a.width * a.height + pix;
 
-    const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, ux, uy, a.depth_min,
-                            a.depth_max);
-    Volume v;
-    v.index = a.sparse_mapping + (size_t)chunk * a.dimz * a.dimy * a.dimx;
-    v.sdf = a.vals_sdf;
-    v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
-    const uint8_t *__restrict__ bricks = a.bricks + (size_t)chunk * a.nbz * a.nby * a.nbx;
-    const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
-    const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
-
-    float ray = r.t0, t_end = r.t1;
-    if (clip) {
-        // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
-        float tin = -__int_as_float(0x7f800000), tout = __int_as_float(0x7f800000);
-        slab(r.camx, r.dx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps, tin, tout);
-        slab(r.camy, r.dy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps, tin, tout);
-        slab(r.camz, r.dz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps, tin, tout);
-        const float margin = 0.0625f;
-        if (!(tin <= tout)) {
-            t_end = ray;  // misses the grid: nothing to march
-        } else {
-            t_end = fminf(t_end, tout + margin);
-            // jump to the last sample at or before tin - margin
-            while (ray < tin - margin - a.inc && ray < t_end) {
-                const float ahead = __fdiv_rn(tin - margin - ray, a.inc);
-                const int want = max(1, min(__float2int_rd(ahead) - 1, 1 << 22));
-                ray = advance_ray(ray, a.inc, want);
-            }
-        }
-    }
-
-    float last_sdf = 0.0f, last_alpha = 0.0f;
-    bool last_ok = false;
     int hit = -1;
     float depth = 0.0f;
 
-    while (ray < t_end) {  // kernel.cu:200
-        const float px = __fmaf_rn(r.dx, ray, r.camx), py = __fmaf_rn(r.dy, ray, r.camy),
-                    pz = __fmaf_rn(r.dz, ray, r.camz);
-        if (skip) {
-            // Brick of floor(p).  If p is at least kBoxEps inside an empty (or out-of-grid) brick on every axis,
-            // the sample's corner (0,0,0) lies in that brick and is absent: the sample is invalid, and so is
-            // every later sample until the ray leaves the shrunken brick.
-            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-            const int bx = __float2int_rd(px) >> kBrickLog2, by = __float2int_rd(py) >> kBrickLog2,
-                      bz = __float2int_rd(pz) >> kBrickLog2;
-            bool empty = true;
-            if ((bx | by | bz) >= 0 && bx < a.nbx && by < a.nby && bz < a.nbz)
-                empty = bricks[(bz * a.nby + by) * a.nbx + bx] == 0;
-            if (empty) {
-                const float lox = (float)(bx << kBrickLog2) + kBoxEps, hix = (float)((bx + 1) << kBrickLog2) - kBoxEps;
-                const float loy = (float)(by << kBrickLog2) + kBoxEps, hiy = (float)((by + 1) << kBrickLog2) - kBoxEps;
-                const float loz = (float)(bz << kBrickLog2) + kBoxEps, hiz = (float)((bz + 1) << kBrickLog2) - kBoxEps;
-                (void)fx; (void)fy; (void)fz;
-                if (px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz) {
-                    float tin = -__int_as_float(0x7f800000), tout = __int_as_float(0x7f800000);
-                    slab(r.camx, r.dx, lox, hix, tin, tout);
-                    slab(r.camy, r.dy, loy, hiy, tin, tout);
-                    slab(r.camz, r.dz, loz, hiz, tin, tout);
-                    int want = 1;
-                    if (tout > ray) want = max(1, min(__float2int_rd(__fdiv_rn(tout - ray, a.inc)) + 1, 1 << 22));
-                    last_ok = false;  // kernel.cu:259
-                    ray = advance_ray(ray, a.inc, want);
-                    continue;
+    if (active) {
+        const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, ux, uy, a.depth_min,
+                                a.depth_max);
+        const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
+        Volume v;
+        v.index = a.sparse_mapping + (size_t)chunk * cells;
+        v.sdf = a.vals_sdf;
+        v.dense = a.dense + (size_t)chunk * cells;
+        v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
+        const uint8_t *__restrict__ skipmap = a.skip + (size_t)chunk * a.n4z * a.n4y * a.n4x;
+        const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
+        const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
+        const bool fast_ok = max(a.dimx, max(a.dimy, a.dimz)) <= kMaxFastDim;
+        const float kInf = CUDART_INF_F;
+        // approximate reciprocals are only used to size jumps; every margin below dwarfs their error
+        const float invx = r.dx != 0.0f ? rcp_approx(r.dx) : 0.0f, invy = r.dy != 0.0f ? rcp_approx(r.dy) : 0.0f,
+                    invz = r.dz != 0.0f ? rcp_approx(r.dz) : 0.0f;
+        Stepper step;
+        step.init(a.inc);
+
+        float ray = r.t0, t_end = r.t1;
+        if (clip) {
+            // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
+            float tin = -kInf, tout = kInf;
+#define SPSG_SLAB(o, d, inv, lo, hi)                                        \
+    if ((d) != 0.0f) {                                                      \
+        const float ta_ = ((lo) - (o)) * (inv), tb_ = ((hi) - (o)) * (inv); \
+        tin = fmaxf(tin, fminf(ta_, tb_));                                  \
+        tout = fminf(tout, fmaxf(ta_, tb_));                                \
+    } else if ((o) < (lo) || (o) > (hi)) {                                  \
+        tin = kInf;                                                         \
+        tout = -kInf;                                                       \
+    }
+            SPSG_SLAB(r.camx, r.dx, invx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps)
+            SPSG_SLAB(r.camy, r.dy, invy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps)
+            SPSG_SLAB(r.camz, r.dz, invz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps)
+#undef SPSG_SLAB
+            const float margin = 0.0625f;
+            if (!(tin <= tout)) {
+                t_end = ray;  // misses the grid: nothing to march
+            } else {
+                t_end = fminf(t_end, tout + margin);
+                // jump to (at most) the last sample before tin - margin
+                while (ray < tin - margin - a.inc && ray < t_end) {
+                    const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, 1 << 22));
+                    ray = step.advance(ray, want);
                 }
             }
         }
-        float dist;
-        int unused;
-        if (sample_sdf<false>(v, px, py, pz, dist, unused)) {
-            if (last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
-                // findIntersectionBisection (:166-187)
-                float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
-                bool ok = true;
-                int nearest = -1;
-#pragma unroll 1
-                for (int k = 0; k < 3; k++) {
-                    c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
-                    float dc;
-                    if (!sample_sdf<true>(v, __fmaf_rn(r.dx, c, r.camx), __fmaf_rn(r.dy, c, r.camy),
-                                          __fmaf_rn(r.dz, c, r.camz), dc, nearest)) {
-                        ok = false;
+
+        float last_sdf = 0.0f, last_alpha = 0.0f;
+        bool last_ok = false;
+
+        for (;;) {  // march to a sign change, refine it, repeat if the refinement is rejected
+            bool crossing = false;
+            float dist = 0.0f;
+            for (;;) {
+                // ---- skip phase: advance to the next sample that has to be evaluated
+                bool cand = false;
+                float px = 0.0f, py = 0.0f, pz = 0.0f;
+                while (ray < t_end && !cand) {  // kernel.cu:200
+                    px = __fmaf_rn(r.dx, ray, r.camx);
+                    py = __fmaf_rn(r.dy, ray, r.camy);
+                    pz = __fmaf_rn(r.dz, ray, r.camz);
+                    cand = true;
+                    if (skip) {
+                        const int ix = __float2int_rd(px), iy = __float2int_rd(py), iz = __float2int_rd(pz);
+                        if ((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
+                            (unsigned)iz < (unsigned)a.dimz) {
+                            const int level = skipmap[((iz >> kFineLog2) * a.n4y + (iy >> kFineLog2)) * a.n4x +
+                                                      (ix >> kFineLog2)];
+                            if (level != 0) {
+                                // p is inside an empty aligned block of edge `size`.  If it is at least kBoxEps inside
+                                // on every axis, the sample's corner (0,0,0) lies in the block and is absent: the sample
+                                // is invalid (kernel.cu:131,259) and so is every later one up to the block's exit.
+                                const int size = 2 << level, mask = ~(size - 1);
+                                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
+                                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
+                                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
+                                if (px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz) {
+                                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
+                                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
+                                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
+                                    const float tout = fminf(tx_, fminf(ty_, tz_));
+                                    int want = 1;
+                                    if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
+                                    last_ok = false;  // kernel.cu:259
+                                    ray = step.advance(ray, want);
+                                    cand = false;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!cand) break;  // ray exhausted
+                // ---- sample phase (converged across the warp)
+                if (sample_sdf(v, fast_ok, px, py, pz, dist)) {
+                    if (last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
+                        crossing = true;
                         break;
                     }
-                    if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+                    last_sdf = dist; last_alpha = ray; last_ok = true;  // :254-256
+                } else {
+                    last_ok = false;  // :259
                 }
-                if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
-                    depth = __fdiv_rn(c, r.d2r);                                                     // :215
-                    hit = nearest;  // == round(cam + alpha*dir), :241-242 (same fma as the last refinement point)
+                ray = __fadd_rn(ray, a.inc);  // :257,:260
+            }
+            if (!crossing) break;  // miss
+            // ---- findIntersectionBisection (:166-187), executed once the warp has converged here
+            float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
+            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+            bool ok = true;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
+                cx = __fmaf_rn(r.dx, c, r.camx);
+                cy = __fmaf_rn(r.dy, c, r.camy);
+                cz = __fmaf_rn(r.dz, c, r.camz);
+                float dc;
+                if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
+                    ok = false;
                     break;
                 }
+                if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+            }
+            if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
+                depth = __fdiv_rn(c, r.d2r);                                                     // :215
+                // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel round(cam + alpha*dir)
+                // (:241-242, same fma).  It is one of the 8 present corners; if rounding ever says otherwise the
+                // reference reads stale registers -- we render the pixel with a zero payload instead.
+                const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
+                hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
+                if (hit >= 0) break;
             }
             last_sdf = dist; last_alpha = ray; last_ok = true;  // :254-256
-        } else {
-            last_ok = false;  // :259
+            ray = __fadd_rn(ray, a.inc);                        // :257
         }
-        ray = __fadd_rn(ray, a.inc);  // :257,:260
     }
 
-    // write-out (kernel.cu:276-285 init, :217-239 hit)
+    // ---- write-out (kernel.cu:276-285 init, :217-239 hit) through shared memory
     const float ninf = __int_as_float(0xff800000);
-    float *oc = a.image_color + gpix * 3, *on = a.image_normal + gpix * 3, *os = a.image_semantic + gpix * 14;
-    if (hit >= 0) {
-        const float *c = a.vals_color + (size_t)hit * 3, *n = a.vals_normal + (size_t)hit * 3,
-                    *s = a.vals_semantic + (size_t)hit * 14;
-        oc[0] = __ldg(c + 0); oc[1] = __ldg(c + 1); oc[2] = __ldg(c + 2);
-        const float n0 = __ldg(n + 0), n1 = __ldg(n + 1), n2 = __ldg(n + 2);
-        const bool zero_normal = (n0 == 0.0f && n1 == 0.0f && n2 == 0.0f);  // :220
-        on[0] = zero_normal ? ninf : n0; on[1] = zero_normal ? ninf : n1; on[2] = zero_normal ? ninf : n2;
-        a.image_depth[gpix] = depth;
+    const int tp = ty * kTileW + tx;
+    float col0 = ninf, col1 = ninf, col2 = ninf, dep = ninf;
+    float sem[14];
 #pragma unroll
-        for (int k = 0; k < 14; k++) os[k] = __ldg(s + k);
+    for (int k = 0; k < 14; k++) sem[k] = ninf;
+    float n0 = ninf, n1 = ninf, n2 = ninf;
+    if (hit >= 0) {
+        const float *c = a.vals_color + (size_t)hit * 3, *n = a.vals_normal + (size_t)hit * 3;
+        col0 = __ldg(c + 0); col1 = __ldg(c + 1); col2 = __ldg(c + 2);
+        const float m0 = __ldg(n + 0), m1 = __ldg(n + 1), m2 = __ldg(n + 2);
+        if (!(m0 == 0.0f && m1 == 0.0f && m2 == 0.0f)) { n0 = m0; n1 = m1; n2 = m2; }  // :220
+        dep = depth;
+        const float2 *s2 = reinterpret_cast<const float2 *>(a.vals_semantic + (size_t)hit * 14);
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const float2 t2 = __ldg(s2 + k);
+            sem[2 * k] = t2.x; sem[2 * k + 1] = t2.y;
+        }
         const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
         const int offset = atomicAdd(a.mapping3dto2d_num + row, 1);                            // :244
         if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;  // :245-247
-    } else {
-        oc[0] = ninf; oc[1] = ninf; oc[2] = ninf;
-        on[0] = ninf; on[1] = ninf; on[2] = ninf;
-        a.image_depth[gpix] = ninf;
-#pragma unroll
-        for (int k = 0; k < 14; k++) os[k] = ninf;
     }
-    if (a.hits) a.hits[gpix] = hit;
+    s_col[tp * 3 + 0] = col0; s_col[tp * 3 + 1] = col1; s_col[tp * 3 + 2] = col2;
+    s_nrm[tp * 3 + 0] = n0; s_nrm[tp * 3 + 1] = n1; s_nrm[tp * 3 + 2] = n2;
+    s_dep[tp] = dep;
+#pragma unroll
+    for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(s_sem + tp * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
+    if (a.hits && active) a.hits[gpix] = hit;
+
+    if (kLoss) {
+        float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (hit >= 0) {
+            const LossArgs &L = a.loss;
+            if (L.target_depth) {  // train.py:635-638
+                const float t = __ldg(L.target_depth + gpix);
+                if (t != 0.0f) { acc[0] = fabsf(__fmul_rn(depth, L.voxelsize) - t); acc[1] = 1.0f; }
+            }
+            if (L.target_color) {  // loss.py:246-257
+                const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+                const float *t = L.target_color + gpix * 3;
+                acc[2] = fabsf(__fadd_rn(__fmul_rn(col0, w), -__fmul_rn(__ldg(t + 0), w))) +
+                         fabsf(__fadd_rn(__fmul_rn(col1, w), -__fmul_rn(__ldg(t + 1), w))) +
+                         fabsf(__fadd_rn(__fmul_rn(col2, w), -__fmul_rn(__ldg(t + 2), w)));
+                acc[3] = 3.0f;
+            }
+            if (L.target_label) {  // train.py:744-746
+                const int y = L.target_label[gpix];
+                if (y < 14 && sem[0] != ninf) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+                    float m = sem[0];
+#pragma unroll
+                    for (int k = 1; k < 14; k++) m = fmaxf(m, sem[k]);
+                    float s = 0.0f, ly = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 14; k++) {
+                        s += expf(sem[k] - m);
+                        if (k == y) ly = sem[k];
+                    }
+                    const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+                    acc[4] = w * (logf(s) + m - ly);
+                    acc[5] = w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            acc[k] = warp_sum(acc[k]);
+            if (lane == 0) s_red[warp][k] = acc[k];
+        }
+    }
+    __syncthreads();
+    if (kLoss && threadIdx.x < 6) {
+        const float t = s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
+        if (t != 0.0f) atomicAdd(a.loss.accum + threadIdx.x, (double)t);
+    }
+    const bool vec = a.vec_ok != 0;
+    store_tile<14>(s_sem, a.image_semantic, img, x0, y0, a.width, a.height, vec);
+    store_tile<3>(s_col, a.image_color, img, x0, y0, a.width, a.height, vec);
+    store_tile<3>(s_nrm, a.image_normal, img, x0, y0, a.width, a.height, vec);
+    store_tile<1>(s_dep, a.image_depth, img, x0, y0, a.width, a.height, vec);
 }
 
-// construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + brick marking + counter reset.
-template <bool kWriteIndex>
-__global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict__ locs, long long n,
-                                                    int32_t *__restrict__ sparse_mapping, uint8_t *__restrict__ bricks,
-                                                    int32_t *__restrict__ num, int views, int dimz, int dimy, int dimx,
-                                                    int nbz, int nby, int nbx) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const longlong4 l = locs[i];  // (z, y, x, chunk)
-    const long long z = l.x, y = l.y, x = l.z, b = l.w;
-    if (kWriteIndex) sparse_mapping[((b * dimz + z) * dimy + y) * dimx + x] = (int32_t)i;
-    if (bricks)
-        bricks[((b * nbz + (z >> kBrickLog2)) * nby + (y >> kBrickLog2)) * nbx + (x >> kBrickLog2)] = 1;
-    if (num)
-        for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
+// loss_out[0..3] = depth, colour, semantic, weighted total; [4..6] = normalisers the backward needs.
+__global__ void finalize_loss_kernel(const double *__restrict__ acc, float *__restrict__ out, float w_depth,
+                                     float w_color, float w_sem, int has_depth, int has_color, int has_sem) {
+    const float ld = has_depth ? (float)(acc[0] / acc[1]) : 0.0f;  // mean over an empty set is NaN, like torch.mean
+    const float lc = has_color ? (float)(acc[2] / acc[3]) : 0.0f;
+    const float ls = has_sem ? (float)(acc[4] / acc[5]) : 0.0f;
+    out[0] = ld; out[1] = lc; out[2] = ls;
+    out[3] = w_depth * ld + w_color * lc + w_sem * ls;
+    out[4] = (float)acc[1]; out[5] = (float)acc[3]; out[6] = (float)acc[5];
+    out[7] = 0.0f;
 }
 
-// Deterministic backward (replaces kernel.cu:365-423): one warp per 32 dense cells; for every present
-// voxel the warp gathers, lane == channel, the gradients of its registered pixels in registration
-// order and writes the per-view means.  Present voxels nobody hit are written as zeros, so no memset
-// of d_* is needed.
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+
 struct BackwardArgs {
-    const float *grad_color, *grad_depth, *grad_normal, *grad_semantic;
+    const float *grad_color, *grad_depth, *grad_normal, *grad_semantic;  // plain variant
+    const float *image_color, *image_depth, *image_semantic;             // fused-loss variant
+    LossArgs loss;
+    const float *loss_out;
+    float w_depth, w_color, w_sem;
+    const float *grad_scale;  // device scalar or NULL (= 1)
     const int32_t *sparse_mapping, *mapping3dto2d, *mapping3dto2d_num;
     float *d_color, *d_depth, *d_normal, *d_semantic;
+    int32_t *list_count;
+    int2 *list;
     int width, height;
     long long cells_per_chunk;
     int num_chunks, views, max_pixels;
     long long num_locs;
 };
 
-__device__ __forceinline__ float load_grad(const BackwardArgs &a, int lane, size_t gpix) {
-    // lane: 0-2 colour, 3 depth, 4-6 normal, 7-20 semantic
-    if (lane < 3) return __ldg(a.grad_color + gpix * 3 + lane);
-    if (lane == 3) return __ldg(a.grad_depth + gpix);
-    if (lane < 7) return __ldg(a.grad_normal + gpix * 3 + (lane - 4));
-    return __ldg(a.grad_semantic + gpix * 14 + (lane - 7));
-}
-
-__global__ void __launch_bounds__(256) raycast_backward_kernel(const BackwardArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Pass 1 (replaces the 4 memsets and the one-block-per-dense-voxel launch of kernel.cu:557-568): one thread per
+// dense cell; present voxels nobody hit get their 21 gradient slots zeroed, hit voxels are appended to a list.
+__global__ void __launch_bounds__(256) backward_scan_kernel(const BackwardArgs a) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = a.cells_per_chunk * a.num_chunks;
-    const long long cell = warp * 32 + lane;
     int idx = -1;
     if (cell < total) idx = __ldg(a.sparse_mapping + cell);
-    unsigned present = __ballot_sync(0xffffffffu, idx >= 0);
-    if (!present) return;
-    const int my_chunk = (int)(cell / a.cells_per_chunk);
+    bool hit = false;
+    if (idx >= 0) {
+        for (int f = 0; f < a.views; f++) hit |= __ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + idx) > 0;
+        if (!hit) {
+            float *c = a.d_color + (size_t)idx * 3, *n = a.d_normal + (size_t)idx * 3;
+            c[0] = 0.0f; c[1] = 0.0f; c[2] = 0.0f;
+            n[0] = 0.0f; n[1] = 0.0f; n[2] = 0.0f;
+            a.d_depth[idx] = 0.0f;
+            float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)idx * 14);
+#pragma unroll
+            for (int k = 0; k < 7; k++) s[k] = make_float2(0.0f, 0.0f);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(idx, (int)(cell / a.cells_per_chunk));
+    }
+}
+
+// Upstream gradient of one pixel for this lane's channel.  Lanes 0-13 semantic, 16-18 colour, 19 depth,
+// 20-22 normal; other lanes idle.
+template <bool kFused>
+__device__ __forceinline__ float pixel_grad(const BackwardArgs &a, int lane, size_t gpix) {
+    if (!kFused) {
+        if (lane < 14) return __ldg(a.grad_semantic + gpix * 14 + lane);
+        if (lane >= 16 && lane < 19) return __ldg(a.grad_color + gpix * 3 + (lane - 16));
+        if (lane == 19) return __ldg(a.grad_depth + gpix);
+        if (lane >= 20 && lane < 23) return __ldg(a.grad_normal + gpix * 3 + (lane - 20));
+        return 0.0f;
+    } else {
+        const LossArgs &L = a.loss;
+        float g = 0.0f;
+        // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
+        const int y = L.target_label ? (int)L.target_label[gpix] : 14;
+        float logit = (lane < 14) ? __ldg(a.image_semantic + gpix * 14 + lane) : -CUDART_INF_F;
+        if (y < 14 && __shfl_sync(0xffffffffu, logit, 0) != -CUDART_INF_F) {  // warp-uniform: one pixel per iteration
+            float m = logit;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float e = (lane < 14) ? expf(logit - m) : 0.0f;
+            float s = e;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane < 14) {
+                const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+                g = a.w_sem * w * (e / s - (lane == y ? 1.0f : 0.0f)) / a.loss_out[6];
+            }
+        }
+        if (lane >= 16 && lane < 19 && L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
+            const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+            const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + gpix * 3 + (lane - 16)), w),
+                                      -__fmul_rn(__ldg(L.target_color + gpix * 3 + (lane - 16)), w));
+            g = a.w_color * ((d > 0.0f) - (d < 0.0f)) * w / a.loss_out[5];
+        }
+        if (lane == 19 && L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
+            const float t = __ldg(L.target_depth + gpix);
+            if (t != 0.0f) {
+                const float d = __fmul_rn(__ldg(a.image_depth + gpix), L.voxelsize) - t;
+                g = a.w_depth * ((d > 0.0f) - (d < 0.0f)) * L.voxelsize / a.loss_out[4];
+            }
+        }
+        return a.grad_scale ? g * __ldg(a.grad_scale) : g;
+    }
+}
+
+// Pass 2: one warp per hit voxel, lane == channel.  For every view the warp walks the voxel's registered pixels
+// in registration order and accumulates grad/cnt (kernel.cu:398-418) -- a fixed order, hence deterministic.
+template <bool kFused>
+__global__ void __launch_bounds__(256) backward_gather_kernel(const BackwardArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const int count = *a.list_count;
     const size_t P = (size_t)a.width * a.height;
-    while (present) {
-        const int src = __ffs(present) - 1;
-        present &= present - 1;
-        const int vidx = __shfl_sync(0xffffffffu, idx, src);
-        const int chunk = __shfl_sync(0xffffffffu, my_chunk, src);
+    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < count; item += warps_total) {
+        const int2 e = a.list[item];
+        const int vidx = e.x, chunk = e.y;
         float acc = 0.0f;
         for (int f = 0; f < a.views; f++) {
             const size_t row = (size_t)f * a.num_locs + vidx;
@@ -426,20 +767,32 @@ __global__ void __launch_bounds__(256) raycast_backward_kernel(const BackwardArg
             for (int t0 = 0; t0 < cnt; t0 += 32) {
                 const int my_pix = (t0 + lane < cnt) ? __ldg(a.mapping3dto2d + row * a.max_pixels + t0 + lane) : 0;
                 const int m = min(32, cnt - t0);
-                for (int t = 0; t < m; t++) {
-                    const int pixel = __shfl_sync(0xffffffffu, my_pix, t);
-                    if (lane < SPSG_GRAD_CHANNELS)
-                        sum = __fadd_rn(sum, __fdiv_rn(load_grad(a, lane, img_base + pixel), fcnt));  // :398-418
+                int t = 0;
+                for (; t + 4 <= m; t += 4) {  // 4 independent gathers in flight, summed in order
+                    const float g0 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t));
+                    const float g1 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 1));
+                    const float g2 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 2));
+                    const float g3 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 3));
+                    sum = __fadd_rn(sum, __fdiv_rn(g0, fcnt));
+                    sum = __fadd_rn(sum, __fdiv_rn(g1, fcnt));
+                    sum = __fadd_rn(sum, __fdiv_rn(g2, fcnt));
+                    sum = __fadd_rn(sum, __fdiv_rn(g3, fcnt));
                 }
+                for (; t < m; t++)
+                    sum = __fadd_rn(sum, __fdiv_rn(pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t)), fcnt));
             }
             acc += sum;
         }
-        if (lane < 3) a.d_color[(size_t)vidx * 3 + lane] = acc;
-        else if (lane == 3) a.d_depth[vidx] = acc;
-        else if (lane < 7) a.d_normal[(size_t)vidx * 3 + (lane - 4)] = acc;
-        else if (lane < SPSG_GRAD_CHANNELS) a.d_semantic[(size_t)vidx * 14 + (lane - 7)] = acc;
+        if (lane < 14) a.d_semantic[(size_t)vidx * 14 + lane] = acc;
+        else if (lane >= 16 && lane < 19) a.d_color[(size_t)vidx * 3 + (lane - 16)] = acc;
+        else if (lane == 19) a.d_depth[vidx] = acc;
+        else if (lane >= 20 && lane < 23) a.d_normal[(size_t)vidx * 3 + (lane - 20)] = acc;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// occupancy raycast
+// ---------------------------------------------------------------------------------------------
 
 // raycast_occ_cuda_kernel (kernel.cu:320-344) + traverseOccGrid (:301-318).
 struct OccArgs {
@@ -452,7 +805,7 @@ struct OccArgs {
     unsigned flags;
 };
 
-__global__ void __launch_bounds__(kTileW *kTileH) raycast_occ_kernel(const OccArgs a) {
+__global__ void __launch_bounds__(kTilePix) raycast_occ_kernel(const OccArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned ux = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
     const unsigned uy = blockIdx.y * kTileH + (warp >> 1) * 4 + (lane >> 3);
@@ -461,22 +814,35 @@ __global__ void __launch_bounds__(kTileW *kTileH) raycast_occ_kernel(const OccAr
     const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, ux, uy, a.depth_min,
                             a.depth_max);
     const uint8_t *__restrict__ occ = a.occ3d + (size_t)img * a.dimz * a.dimy * a.dimx;
+    Stepper step;
+    step.init(a.inc);
     float ray = r.t0, t_end = r.t1;
     if (!(a.flags & SPSG_FLAG_NO_CLIP)) {
         // nearest voxel is inside the grid only for p in (-0.5, dim-0.5)
-        float tin = -__int_as_float(0x7f800000), tout = __int_as_float(0x7f800000);
-        slab(r.camx, r.dx, -0.5f - kBoxEps, (float)a.dimx - 0.5f + kBoxEps, tin, tout);
-        slab(r.camy, r.dy, -0.5f - kBoxEps, (float)a.dimy - 0.5f + kBoxEps, tin, tout);
-        slab(r.camz, r.dz, -0.5f - kBoxEps, (float)a.dimz - 0.5f + kBoxEps, tin, tout);
+        const float kInf = CUDART_INF_F;
+        float tin = -kInf, tout = kInf;
+        const float o[3] = {r.camx, r.camy, r.camz}, d[3] = {r.dx, r.dy, r.dz};
+        const float hi[3] = {(float)a.dimx - 0.5f + kBoxEps, (float)a.dimy - 0.5f + kBoxEps, (float)a.dimz - 0.5f + kBoxEps};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float lo = -0.5f - kBoxEps;
+            if (d[k] != 0.0f) {
+                const float inv = rcp_approx(d[k]);
+                const float ta = (lo - o[k]) * inv, tb = (hi[k] - o[k]) * inv;
+                tin = fmaxf(tin, fminf(ta, tb));
+                tout = fminf(tout, fmaxf(ta, tb));
+            } else if (o[k] < lo || o[k] > hi[k]) {
+                tin = kInf; tout = -kInf;
+            }
+        }
         const float margin = 0.0625f;
         if (!(tin <= tout)) {
             t_end = ray;
         } else {
             t_end = fminf(t_end, tout + margin);
             while (ray < tin - margin - a.inc && ray < t_end) {
-                const float ahead = __fdiv_rn(tin - margin - ray, a.inc);
-                const int want = max(1, min(__float2int_rd(ahead) - 1, 1 << 22));
-                ray = advance_ray(ray, a.inc, want);
+                const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, 1 << 22));
+                ray = step.advance(ray, want);
             }
         }
     }
@@ -494,6 +860,10 @@ __global__ void __launch_bounds__(kTileW *kTileH) raycast_occ_kernel(const OccAr
     a.occ2d[(size_t)img * a.width * a.height + uy * a.width + ux] = out;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
 int check_params(const spsg_raycast_params *p) {
     if (!p) return fail(SPSG_ERR_INVALID_ARGUMENT, "params is NULL");
     if (p->width <= 0 || p->height <= 0) return fail(SPSG_ERR_INVALID_ARGUMENT, "width/height must be positive");
@@ -508,11 +878,25 @@ int check_params(const spsg_raycast_params *p) {
     return SPSG_OK;
 }
 
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+LossArgs make_loss_args(const spsg_loss_targets *t, double *accum) {
+    LossArgs L;
+    memset(&L, 0, sizeof(L));
+    if (t) {
+        L.target_depth = t->target_depth; L.target_color = t->target_color; L.weight_color = t->weight_color;
+        L.target_label = t->target_label; L.class_weight = t->class_weight; L.voxelsize = t->voxelsize;
+    }
+    L.accum = accum;
+    return L;
+}
+
 int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *sparse_mapping, const int64_t *locs,
                    const float *vals_sdf, const float *vals_color, const float *vals_normal,
                    const float *vals_semantic, const float *view_matrix, const float *intrinsics, float *image_color,
                    float *image_depth, float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
-                   int32_t *mapping3dto2d_num, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                   int32_t *mapping3dto2d_num, const spsg_loss_targets *targets, float *loss_out, void *workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
     if (int rc = check_params(p)) return rc;
     if (p->max_pixels_per_voxel <= 0) return fail(SPSG_ERR_INVALID_ARGUMENT, "max_pixels_per_voxel must be positive");
     if (!sparse_mapping || !view_matrix || !intrinsics || !image_color || !image_depth || !image_normal ||
@@ -520,45 +904,123 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
     if (p->num_locs > 0 && (!locs || !vals_sdf || !vals_color || !vals_normal || !vals_semantic))
         return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL voxel tensor pointer");
+    if (!aligned16(view_matrix) || !aligned16(intrinsics))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "view_matrix / intrinsics must be 16-byte aligned");
+    if (p->num_locs > 0 && ((reinterpret_cast<uintptr_t>(vals_semantic) & 7u) || (reinterpret_cast<uintptr_t>(locs) & 15u)))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "vals_semantic must be 8-byte and locs 16-byte aligned");
+    if (targets && !loss_out) return fail(SPSG_ERR_INVALID_ARGUMENT, "loss_out is NULL");
     const Layout L = make_layout(p);
     if (!workspace || workspace_bytes < L.total) return fail(SPSG_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(SPSG_ERR_INVALID_ARGUMENT, "workspace must be 256-byte aligned");
     uint8_t *ws = (uint8_t *)workspace;
-    uint8_t *bricks = ws + L.brick_off;
+    float *dense = (float *)(ws + L.dense_off);
+    uint8_t *skip = ws + L.skip_off;
+    double *accum = (double *)(ws + L.loss_off);
     const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
 
     if (build_index) CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));  // kernel.cu:515
-    CUDA_TRY(cudaMemsetAsync(bricks, 0, L.brick_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(dense, 0xff, L.dense_bytes, st));  // 0xffffffff is a NaN: every voxel absent
+    CUDA_TRY(cudaMemsetAsync(skip, 0, L.skip_bytes, st));
+    if (targets) CUDA_TRY(cudaMemsetAsync(accum, 0, 8 * sizeof(double), st));
     if (p->num_locs > 0) {
         const unsigned blocks = (unsigned)((p->num_locs + 255) / 256);
         if (build_index)
-            index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, bricks,
-                                                       mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
-                                                       p->dimx, L.nbz, L.nby, L.nbx);
+            index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
+                                                       dense, skip, mapping3dto2d_num, p->views_per_chunk, p->dimz,
+                                                       p->dimy, p->dimx, L.n4z, L.n4y, L.n4x);
         else
-            index_kernel<false><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, bricks,
-                                                        mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
-                                                        p->dimx, L.nbz, L.nby, L.nbx);
+            index_kernel<false><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
+                                                        dense, skip, mapping3dto2d_num, p->views_per_chunk, p->dimz,
+                                                        p->dimy, p->dimx, L.n4z, L.n4y, L.n4x);
+        CUDA_TRY(cudaGetLastError());
+    }
+    {
+        const int sbx = (L.n4x + kSuper - 1) / kSuper, sby = (L.n4y + kSuper - 1) / kSuper,
+                  sbz = (L.n4z + kSuper - 1) / kSuper;
+        skip_hierarchy_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(skip, L.n4z, L.n4y, L.n4x,
+                                                                                           sbz, sby, sbx);
         CUDA_TRY(cudaGetLastError());
     }
     ForwardArgs a;
+    memset(&a, 0, sizeof(a));
     a.sparse_mapping = sparse_mapping;
     a.vals_sdf = vals_sdf; a.vals_color = vals_color; a.vals_normal = vals_normal; a.vals_semantic = vals_semantic;
     a.view_matrix = view_matrix; a.intrinsics = intrinsics;
     a.image_color = image_color; a.image_depth = image_depth; a.image_normal = image_normal;
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
-    a.bricks = bricks;
+    a.dense = dense; a.skip = skip;
     a.hits = (p->flags & SPSG_FLAG_RECORD_HITS) ? (int32_t *)(ws + L.hits_off) : nullptr;
     a.width = p->width; a.height = p->height;
     a.depth_min = p->depth_min; a.depth_max = p->depth_max; a.thresh = p->thresh_sample_dist; a.inc = p->ray_increment;
     a.dimx = p->dimx; a.dimy = p->dimy; a.dimz = p->dimz;
-    a.nbx = L.nbx; a.nby = L.nby; a.nbz = L.nbz;
+    a.n4x = L.n4x; a.n4y = L.n4y; a.n4z = L.n4z;
     a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
     a.num_locs = p->num_locs;
     a.flags = p->flags;
+    a.vec_ok = (p->width % 4 == 0) && aligned16(image_color) && aligned16(image_depth) && aligned16(image_normal) &&
+               aligned16(image_semantic);
+    a.loss = make_loss_args(targets, accum);
     const dim3 grid((p->width + kTileW - 1) / kTileW, (p->height + kTileH - 1) / kTileH,
                     p->num_chunks * p->views_per_chunk);
-    raycast_forward_kernel<<<grid, kTileW * kTileH, 0, st>>>(a);
+    if (targets) {
+        raycast_forward_kernel<true><<<grid, kTilePix, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
+                                              targets->weight_semantic, targets->target_depth != nullptr,
+                                              targets->target_color != nullptr, targets->target_label != nullptr);
+    } else {
+        raycast_forward_kernel<false><<<grid, kTilePix, 0, st>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_img_color, const float *g_or_img_depth,
+                    const float *grad_normal, const float *g_or_img_semantic, const spsg_loss_targets *targets,
+                    const float *loss_out, const float *grad_scale, const int32_t *sparse_mapping,
+                    const int32_t *mapping3dto2d, const int32_t *mapping3dto2d_num, float *d_color, float *d_depth,
+                    float *d_normal, float *d_semantic, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (int rc = check_params(p)) return rc;
+    if (!g_or_img_color || !g_or_img_depth || !g_or_img_semantic || (!fused && !grad_normal) || !sparse_mapping ||
+        !mapping3dto2d || !mapping3dto2d_num)
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+    if (fused && (!targets || !loss_out)) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL loss targets");
+    if (p->num_locs == 0) return SPSG_OK;
+    if (!d_color || !d_depth || !d_normal || !d_semantic) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer");
+    if (reinterpret_cast<uintptr_t>(d_semantic) & 7u) return fail(SPSG_ERR_INVALID_ARGUMENT, "d_semantic must be 8-byte aligned");
+    const Layout L = make_layout(p);
+    if (!workspace || workspace_bytes < L.total) return fail(SPSG_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
+    uint8_t *ws = (uint8_t *)workspace;
+    BackwardArgs a;
+    memset(&a, 0, sizeof(a));
+    if (fused) {
+        a.image_color = g_or_img_color; a.image_depth = g_or_img_depth; a.image_semantic = g_or_img_semantic;
+        a.loss = make_loss_args(targets, nullptr);
+        a.loss_out = loss_out;
+        a.w_depth = targets->weight_depth; a.w_color = targets->weight_color_loss; a.w_sem = targets->weight_semantic;
+        a.grad_scale = grad_scale;
+    } else {
+        a.grad_color = g_or_img_color; a.grad_depth = g_or_img_depth; a.grad_normal = grad_normal;
+        a.grad_semantic = g_or_img_semantic;
+    }
+    a.sparse_mapping = sparse_mapping; a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
+    a.d_color = d_color; a.d_depth = d_depth; a.d_normal = d_normal; a.d_semantic = d_semantic;
+    a.list_count = (int32_t *)(ws + L.list_off);
+    a.list = (int2 *)(ws + L.list_off + 256);
+    a.width = p->width; a.height = p->height;
+    a.cells_per_chunk = (long long)p->dimz * p->dimy * p->dimx;
+    a.num_chunks = p->num_chunks; a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
+    a.num_locs = p->num_locs;
+    CUDA_TRY(cudaMemsetAsync(a.list_count, 0, sizeof(int32_t), st));
+    const long long cells = a.cells_per_chunk * a.num_chunks;
+    backward_scan_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned blocks = (unsigned)(sms * 8);  // 8 resident 256-thread CTAs per SM, grid-stride over the list
+    if (fused) backward_gather_kernel<true><<<blocks, 256, 0, st>>>(a);
+    else backward_gather_kernel<false><<<blocks, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }
@@ -567,7 +1029,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
 
 extern "C" {
 
-const char *spsg_version(void) { return "spsg_raycast_b200 0.1 (sm_100a)"; }
+const char *spsg_version(void) { return "spsg_raycast_b200 0.2 (sm_100a)"; }
 const char *spsg_last_error(void) { return g_err; }
 
 size_t spsg_workspace_bytes(const spsg_raycast_params *p) {
@@ -585,7 +1047,8 @@ int spsg_build_index(const int64_t *locs, int64_t num_locs, int32_t *sparse_mapp
     CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));
     if (num_locs > 0) {
         index_kernel<true><<<(unsigned)((num_locs + 255) / 256), 256, 0, st>>>(
-            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, 0, dimz, dimy, dimx, 0, 0, 0);
+            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, nullptr, nullptr, 0, dimz, dimy, dimx,
+            0, 0, 0);
         CUDA_TRY(cudaGetLastError());
     }
     return SPSG_OK;
@@ -599,8 +1062,8 @@ int spsg_raycast_forward(const spsg_raycast_params *p, const int32_t *sparse_map
                          void *stream) {
     return launch_forward(p, false, const_cast<int32_t *>(sparse_mapping), locs, vals_sdf, vals_color, vals_normal,
                           vals_semantic, view_matrix, intrinsics, image_color, image_depth, image_normal,
-                          image_semantic, mapping3dto2d, mapping3dto2d_num, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+                          image_semantic, mapping3dto2d, mapping3dto2d_num, nullptr, nullptr, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
 }
 
 int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t *sparse_mapping, const int64_t *locs,
@@ -611,39 +1074,25 @@ int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t *sparse_m
                                  size_t workspace_bytes, void *stream) {
     return launch_forward(p, true, sparse_mapping, locs, vals_sdf, vals_color, vals_normal, vals_semantic, view_matrix,
                           intrinsics, image_color, image_depth, image_normal, image_semantic, mapping3dto2d,
-                          mapping3dto2d_num, workspace, workspace_bytes, (cudaStream_t)stream);
+                          mapping3dto2d_num, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int spsg_raycast_backward(const spsg_raycast_params *p, const float *grad_color, const float *grad_depth,
                           const float *grad_normal, const float *grad_semantic, const int32_t *sparse_mapping,
                           const int32_t *mapping3dto2d, const int32_t *mapping3dto2d_num, float *d_color,
-                          float *d_depth, float *d_normal, float *d_semantic, void *stream) {
-    if (int rc = check_params(p)) return rc;
-    if (!grad_color || !grad_depth || !grad_normal || !grad_semantic || !sparse_mapping || !mapping3dto2d ||
-        !mapping3dto2d_num)
-        return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
-    if (p->num_locs == 0) return SPSG_OK;
-    if (!d_color || !d_depth || !d_normal || !d_semantic) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer");
-    BackwardArgs a;
-    a.grad_color = grad_color; a.grad_depth = grad_depth; a.grad_normal = grad_normal; a.grad_semantic = grad_semantic;
-    a.sparse_mapping = sparse_mapping; a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
-    a.d_color = d_color; a.d_depth = d_depth; a.d_normal = d_normal; a.d_semantic = d_semantic;
-    a.width = p->width; a.height = p->height;
-    a.cells_per_chunk = (long long)p->dimz * p->dimy * p->dimx;
-    a.num_chunks = p->num_chunks; a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
-    a.num_locs = p->num_locs;
-    cudaStream_t st = (cudaStream_t)stream;
-    const long long warps = (a.cells_per_chunk * a.num_chunks + 31) / 32;
-    const unsigned blocks = (unsigned)((warps + 7) / 8);
-    raycast_backward_kernel<<<blocks, 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return SPSG_OK;
+                          float *d_depth, float *d_normal, float *d_semantic, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+    return launch_backward(p, false, grad_color, grad_depth, grad_normal, grad_semantic, nullptr, nullptr, nullptr,
+                           sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color, d_depth, d_normal, d_semantic,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int spsg_raycast_occ(const spsg_raycast_params *p, const uint8_t *occ3d, uint8_t *occ2d, const float *view_matrix,
                      const float *intrinsics, void *stream) {
     if (int rc = check_params(p)) return rc;
     if (!occ3d || !occ2d || !view_matrix || !intrinsics) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
+    if (!aligned16(view_matrix) || !aligned16(intrinsics))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "view_matrix / intrinsics must be 16-byte aligned");
     OccArgs a;
     a.occ3d = occ3d; a.occ2d = occ2d; a.view_matrix = view_matrix; a.intrinsics = intrinsics;
     a.width = p->width; a.height = p->height;
@@ -651,22 +1100,31 @@ int spsg_raycast_occ(const spsg_raycast_params *p, const uint8_t *occ3d, uint8_t
     a.dimx = p->dimx; a.dimy = p->dimy; a.dimz = p->dimz;
     a.flags = p->flags;
     const dim3 grid((p->width + kTileW - 1) / kTileW, (p->height + kTileH - 1) / kTileH, p->num_chunks);
-    raycast_occ_kernel<<<grid, kTileW * kTileH, 0, (cudaStream_t)stream>>>(a);
+    raycast_occ_kernel<<<grid, kTilePix, 0, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }
 
-int spsg_raycast_forward_loss(const spsg_raycast_params *, int32_t *, const int64_t *, const float *, const float *,
-                              const float *, const float *, const float *, const float *, float *, float *, float *,
-                              float *, int32_t *, int32_t *, const spsg_loss_targets *, float *, void *, size_t,
-                              void *) {
-    return fail(SPSG_ERR_INVALID_ARGUMENT, "spsg_raycast_forward_loss: not built yet");
+int spsg_raycast_forward_loss(const spsg_raycast_params *p, int32_t *sparse_mapping, const int64_t *locs,
+                              const float *vals_sdf, const float *vals_color, const float *vals_normal,
+                              const float *vals_semantic, const float *view_matrix, const float *intrinsics,
+                              float *image_color, float *image_depth, float *image_normal, float *image_semantic,
+                              int32_t *mapping3dto2d, int32_t *mapping3dto2d_num, const spsg_loss_targets *t,
+                              float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!t) return fail(SPSG_ERR_INVALID_ARGUMENT, "loss targets are NULL");
+    return launch_forward(p, true, sparse_mapping, locs, vals_sdf, vals_color, vals_normal, vals_semantic, view_matrix,
+                          intrinsics, image_color, image_depth, image_normal, image_semantic, mapping3dto2d,
+                          mapping3dto2d_num, t, loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int spsg_raycast_backward_loss(const spsg_raycast_params *, const float *, const float *, const float *,
-                               const spsg_loss_targets *, const float *, float, const int32_t *, const int32_t *,
-                               const int32_t *, float *, float *, float *, float *, void *) {
-    return fail(SPSG_ERR_INVALID_ARGUMENT, "spsg_raycast_backward_loss: not built yet");
+int spsg_raycast_backward_loss(const spsg_raycast_params *p, const float *image_color, const float *image_depth,
+                               const float *image_semantic, const spsg_loss_targets *t, const float *loss_out,
+                               const float *grad_scale, const int32_t *sparse_mapping, const int32_t *mapping3dto2d,
+                               const int32_t *mapping3dto2d_num, float *d_color, float *d_depth, float *d_normal,
+                               float *d_semantic, void *workspace, size_t workspace_bytes, void *stream) {
+    return launch_backward(p, true, image_color, image_depth, nullptr, image_semantic, t, loss_out, grad_scale,
+                           sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color, d_depth, d_normal, d_semantic,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

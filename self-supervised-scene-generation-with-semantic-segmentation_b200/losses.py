@@ -1,0 +1,132 @@
+"""2D view-guided losses fused into the raycast.
+
+``render_with_2d_losses`` renders the predicted chunk exactly like ``RaycastRGBD.forward`` and, in the same
+kernel, accumulates the reference's three 2D loss terms
+
+    depth L1      mean |depth * voxelsize - images_depth|  over (hit & images_depth != 0)    train.py:635-638
+    colour L1     mean |colour * w - target * w|            over hit pixels x 3 channels      loss.py:246-257
+    semantic CE   sum w[y] * nll / sum w[y]                 over (hit & label < 14)           train.py:744-746
+
+Its backward never materialises the four gradient images: every registered pixel's upstream gradient is
+recomputed from (rendering, target, normalisers) inside the per-voxel gather.  No CPU path.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _native as N
+from . import raycast_rgbd_cuda as rc
+
+
+def labels_from_render(raycast_semantic):
+    """target2d_label of train.py:614-616 / pred2d_label of :749-752: argmax over cat(render, ones) as uint8,
+    14 = miss or unlabeled.  (Plain tensor ops; not on the timed path.)"""
+    best, arg = raycast_semantic.max(dim=-1)
+    return torch.where(best >= 1.0, arg, torch.full_like(arg, 14)).to(torch.uint8)
+
+
+def _targets_struct(images, h, w, target_depth, target_color, weight_color, target_label, class_weight, voxelsize,
+                    weights):
+    def chk(t, numel, dtype, name):
+        if t is None:
+            return None
+        if not t.is_cuda or not t.is_contiguous() or t.dtype != dtype or t.numel() != numel:
+            raise RuntimeError("%s must be a contiguous CUDA %s tensor with %d elements" % (name, dtype, numel))
+        return t
+    px = images * h * w
+    t = N.LossTargets(N.ptr(chk(target_depth, px, torch.float32, "target_depth")),
+                      N.ptr(chk(target_color, 3 * px, torch.float32, "target_color")),
+                      N.ptr(chk(weight_color, px, torch.float32, "weight_color")),
+                      N.ptr(chk(target_label, px, torch.uint8, "target_label")),
+                      N.ptr(chk(class_weight, 14, torch.float32, "class_weight")),
+                      float(voxelsize), float(weights[0]), float(weights[1]), float(weights[2]))
+    return t
+
+
+class FusedRaycastLossFunction(Function):
+    @staticmethod
+    def forward(ctx, raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix,
+                intrinsic_params, target_depth, target_color, weight_color, target_label, class_weight, voxelsize,
+                weights):
+        m = raycaster
+        images = view_matrix.shape[0]
+        views = max(1, images // m.batch_size)
+        if images != views * m.batch_size or views > m.max_num_frames:
+            raise RuntimeError("view_matrix has %d images: expected batch_size (%d) x views <= max_num_frames (%d)"
+                               % (images, m.batch_size, m.max_num_frames))
+        n = locs.shape[0]
+        if n * views > m.mapping3dto2d.shape[0]:
+            raise RuntimeError("too many voxels for raycast (%d x %d views > %d rows)" % (n, views, m.mapping3dto2d.shape[0]))
+        for t, name in ((locs, "locs"), (vals_sdf, "vals_sdf"), (vals_colors, "vals_colors"),
+                        (vals_normals, "vals_normals"), (vals_semantic, "vals_semantic"), (view_matrix, "view_matrix"),
+                        (intrinsic_params, "intrinsic_params")):
+            rc._check_input(t, name)
+        p = N.make_params(m.width, m.height, m.depth_min, m.depth_max, m.thresh_sample_dist, m.ray_increment,
+                          m.dims3d[2], m.dims3d[1], m.dims3d[0], m.batch_size, views, m.mapping3dto2d.shape[1], n,
+                          m.flags)
+        tg = _targets_struct(images, m.height, m.width, target_depth, target_color, weight_color, target_label,
+                             class_weight, voxelsize, weights)
+        dev = vals_sdf.device
+        if getattr(m, "loss_out", None) is None:
+            m.loss_out = torch.zeros(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+        with torch.cuda.device(dev):
+            ws = rc.workspace(dev, N.workspace_bytes(p))
+            N.check(N.lib.spsg_raycast_forward_loss(
+                ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
+                N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
+                N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_normal), N.ptr(m.image_semantic),
+                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(m.loss_out), N.ptr(ws),
+                ws.numel(), rc._stream(dev)))
+        ctx.raycaster, ctx.params, ctx.targets, ctx.n = m, p, tg, n
+        # keep the target tensors alive until backward (the struct only holds raw pointers)
+        ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
+        losses = m.loss_out[:4].clone()
+        ctx.mark_non_differentiable(m.image_color, m.image_depth, m.image_normal, m.image_semantic)
+        imgs = (m.image_color, m.image_depth, m.image_normal, m.image_semantic)
+        if images != m.image_depth.shape[0]:
+            imgs = tuple(i[:images] for i in imgs)
+            ctx.mark_non_differentiable(*imgs)
+        terms = losses[:3]
+        ctx.mark_non_differentiable(terms)
+        return (losses[3], terms) + imgs
+
+    @staticmethod
+    def backward(ctx, grad_total, grad_terms, *unused):
+        m, p, tg, n = ctx.raycaster, ctx.params, ctx.targets, ctx.n
+        dev = m.image_depth.device
+        scale = grad_total.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            ws = rc.workspace(dev, N.workspace_bytes(p))
+            N.check(N.lib.spsg_raycast_backward_loss(
+                ctypes.byref(p), N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_semantic),
+                ctypes.byref(tg), N.ptr(m.loss_out), N.ptr(scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),
+                N.ptr(m.mapping3dto2d_num), N.ptr(m.d_color), N.ptr(m.d_depth), N.ptr(m.d_normal), N.ptr(m.d_semantic),
+                N.ptr(ws), ws.numel(), rc._stream(dev)))
+        return (None, None, m.d_depth[:n], m.d_color[:n], m.d_normal[:n], m.d_semantic[:n]) + (None,) * 9
+
+
+def render_with_2d_losses(raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantics, view_matrix,
+                          intrinsic_params, images_depth=None, images_color=None, weight_color=None,
+                          target2d_label=None, weight_semantic_class=None, voxelsize=0.02,
+                          weight_depth_loss=1.0, weight_color_loss=1.0, weight_semantic_loss=1.0):
+    """Fused prediction raycast + 2D losses (train.py:626-643, 744-746 in one kernel pair).
+
+    raycaster        a ``RaycastRGBD`` (owns the image / mapping / gradient buffers, as in the reference)
+    images_depth     (I,H,W) or (I,1,H,W) metres, 0 = hole;  None switches the depth term off
+    images_color     (I,H,W,3) channels-last (the reference passes images_color.permute(0,2,3,1)); None = off
+    weight_color     (I,H,W) or (I,1,H,W) per-pixel colour weight or None
+    target2d_label   (I,H,W) or (I,H,W,1) uint8, 14 = ignore; None switches the semantic term off
+    Returns (total, terms[3] = (depth, colour, semantic), (color, depth, normal, semantic) renderings).
+    ``total = weight_depth_loss*depth + weight_color_loss*colour + weight_semantic_loss*semantic``; gradients flow
+    from ``total`` only (``terms`` are reported values, like the ``.item()`` logging in train.py)."""
+    if vals_semantics is None:
+        vals_semantics = torch.zeros(vals_sdf.shape[0], 14, device=vals_sdf.device)
+    out = FusedRaycastLossFunction.apply(
+        raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantics, view_matrix, intrinsic_params,
+        None if images_depth is None else images_depth.contiguous(),
+        None if images_color is None else images_color.contiguous(),
+        None if weight_color is None else weight_color.contiguous(),
+        None if target2d_label is None else target2d_label.contiguous(),
+        weight_semantic_class, voxelsize, (weight_depth_loss, weight_color_loss, weight_semantic_loss))
+    return out[0], out[1], out[2:]

@@ -137,10 +137,11 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                       max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n)
     dev = grad_color.device
     with torch.cuda.device(dev):
+        ws = workspace(dev, N.workspace_bytes(p))
         N.check(N.lib.spsg_raycast_backward(ctypes.byref(p), N.ptr(grad_color), N.ptr(grad_depth), N.ptr(grad_normal),
                                             N.ptr(grad_semantic), N.ptr(sparse_mapping), N.ptr(mapping3dto2d),
                                             N.ptr(mapping3dto2d_num), N.ptr(d_color), N.ptr(d_depth),
-                                            N.ptr(d_normals), N.ptr(d_semantic), _stream(dev)))
+                                            N.ptr(d_normals), N.ptr(d_semantic), N.ptr(ws), ws.numel(), _stream(dev)))
 
 
 def raycast_occ(occ3d, occ2d, viewMatrixInv, intrinsicParams, opts, flags=0):

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Aggregate an ncu source-page CSV (SASS view) per CUDA source line.
+
+usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring> [top]
+Line numbers come from `nvdisasm -g` of the library's current cubin, matched to the ncu rows by instruction order,
+so the report must have been captured from the same build."""
+import csv, io, os, re, subprocess, sys, tempfile
+
+rep, kern = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "lib", "libspsg_raycast.so")
+tmp = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL)
+cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+lines, cur, infn, inl = [], None, False, ""
+for l in dis.splitlines():
+    if l.startswith("\t.section\t.text."):
+        infn = kern in l
+    if not infn:
+        continue
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
+    if m:
+        cur = int(m.group(2)); inl = m.group(3); continue
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
+        lines.append(cur)
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
+hdr = rows[hi]; body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+iI, iS, iSrc, iT = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source"), hdr.index("Thread Instructions Executed")
+print("sass rows %d, disasm instrs %d" % (len(body), len(lines)))
+agg = {}
+tot = totS = 0
+for k, r in enumerate(body):
+    ln = lines[k] if k < len(lines) else -1
+    a = agg.setdefault(ln, [0, 0, 0])
+    a[0] += int(r[iI]); a[1] += int(r[iS]); a[2] += int(r[iT]); tot += int(r[iI]); totS += int(r[iS])
+src = open(os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "csrc", "spsg_raycast.cu")).read().splitlines()
+print("total warp instr %d, samples %d" % (tot, totS))
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    text = src[ln - 1].strip()[:100] if ln and 0 < ln <= len(src) else "?"
+    print("%6.2f%% instr  %6.2f%% samples  thr/instr %4.1f  L%-4s %s" % (100.0 * a[0] / tot, 100.0 * a[1] / max(totS, 1), a[2] / max(a[0], 1), ln, text))
