@@ -31,7 +31,7 @@ def test_argument_validation_without_a_gpu():
     bad = N.make_params(0, 256, 5, 300, 45.45, 0.9, 64, 64, 128, 1, 1, 64, 0)
     assert N.lib.spsg_workspace_bytes(ctypes.byref(bad)) == 0
     assert b"width" in N.lib.spsg_last_error()
-    rc = N.lib.spsg_raycast_backward(ctypes.byref(p), *([None] * 12))
+    rc = N.lib.spsg_raycast_backward(ctypes.byref(p), *([None] * 12), 0, None)
     assert rc == 1 and b"NULL" in N.lib.spsg_last_error()
 
 
