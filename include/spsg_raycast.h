@@ -92,6 +92,13 @@ typedef struct spsg_loss_targets {
 SPSG_API const char *spsg_version(void);
 SPSG_API const char *spsg_last_error(void);
 
+/* Measurement aid for bench.py's roofline leg: while enabled, every raycast forward kernel (which = 0) and backward
+ * gather kernel (which = 1) is bracketed by CUDA events on its launch stream; spsg_timing_read waits for the
+ * recorded launches, returns their summed device time and count, and clears the record.  Do not enable during
+ * stream capture. */
+SPSG_API void spsg_timing_enable(int on);
+SPSG_API int spsg_timing_read(int which, double *total_ms, int *launches);
+
 /* Scratch shared by forward and backward of one call pair: dense SDF brick (4*B*Dz*Dy*Dx bytes), skip-level map,
  * hit-voxel list, loss accumulators, optional per-pixel hit records.  Must be 256-byte aligned. */
 SPSG_API size_t spsg_workspace_bytes(const spsg_raycast_params *p);

@@ -19,7 +19,7 @@ SPSG_LOSS_OUT_FLOATS = 8
 EXPORTS = (
     "spsg_version", "spsg_last_error", "spsg_workspace_bytes", "spsg_build_index", "spsg_raycast_forward",
     "spsg_raycast_forward_indexed", "spsg_raycast_backward", "spsg_raycast_occ", "spsg_raycast_forward_loss",
-    "spsg_raycast_backward_loss",
+    "spsg_raycast_backward_loss", "spsg_timing_enable", "spsg_timing_read",
 )
 
 
@@ -77,6 +77,10 @@ def _load():
     lib.spsg_raycast_forward_loss.argtypes = [pp] + [vp] * 14 + [lt, vp, vp, sz, vp]
     lib.spsg_raycast_backward_loss.restype = ctypes.c_int
     lib.spsg_raycast_backward_loss.argtypes = [pp, vp, vp, vp, lt, vp, vp] + [vp] * 7 + [vp, sz, vp]
+    lib.spsg_timing_enable.restype = None
+    lib.spsg_timing_enable.argtypes = [ctypes.c_int]
+    lib.spsg_timing_read.restype = ctypes.c_int
+    lib.spsg_timing_read.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
     return lib
 
 
@@ -113,3 +117,15 @@ def workspace_bytes(params):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def timing_enable(on):
+    lib.spsg_timing_enable(1 if on else 0)
+
+
+def timing_read(which):
+    """(total_ms, launches) of the raycast forward kernel (which=0) / backward gather kernel (which=1) since the last
+    read."""
+    ms, cnt = ctypes.c_double(0.0), ctypes.c_int(0)
+    check(lib.spsg_timing_read(int(which), ctypes.byref(ms), ctypes.byref(cnt)))
+    return ms.value, cnt.value

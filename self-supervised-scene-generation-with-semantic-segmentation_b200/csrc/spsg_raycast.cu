@@ -22,6 +22,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "spsg_raycast.h"
 
 namespace {
@@ -32,6 +35,7 @@ constexpr int kSuper = 8;                // hierarchy kernel handles 8^3 fine bl
 constexpr float kBoxEps = 1.0f / 64.0f;  // shrink of skip boxes; >> every fp32 error term
 constexpr float kFracGuard = 1.0f / 256.0f;  // fast corner path needs frac(p) in [guard, 1-guard]
 constexpr int kMaxFastDim = 8192;        // fast corner path proven for coordinates < 2^13
+constexpr int kLossSlots = 64;           // copies of the loss accumulators (spreads atomic contention)
 
 thread_local char g_err[512] = "";
 
@@ -51,13 +55,40 @@ int fail_cuda(cudaError_t e, const char *where) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Optional per-kernel timing (bench.py's roofline leg): CUDA event pairs recorded on the launch stream around the
+// two dominant kernels.  Off by default; not usable during stream capture.
+struct EventPair { cudaEvent_t a, b; };
+bool g_timing = false;
+std::vector<EventPair> g_ev[2];  // 0 = raycast_forward_kernel, 1 = backward_gather_kernel
+std::mutex g_timing_mu;
+
+struct ScopedKernelTimer {
+    int which; cudaStream_t st; EventPair ev; bool on;
+    ScopedKernelTimer(int w, cudaStream_t s) : which(w), st(s), on(g_timing) {
+        if (on) {
+            on = cudaEventCreate(&ev.a) == cudaSuccess && cudaEventCreate(&ev.b) == cudaSuccess;
+            if (on) cudaEventRecord(ev.a, st);
+        }
+    }
+    ~ScopedKernelTimer() {
+        if (on) {
+            cudaEventRecord(ev.b, st);
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            g_ev[which].push_back(ev);
+        }
+    }
+};
+
 // Workspace layout (caller-owned scratch, see spsg_workspace_bytes)
 struct Layout {
     int n4x, n4y, n4z;  // fine skip blocks per axis
     size_t dense_off, dense_bytes;  // f32 [B][Dz][Dy][Dx], NaN = absent
-    size_t skip_off, skip_bytes;    // u8  [B][n4z][n4y][n4x] skip level (0 = occupied)
+    size_t skip_off, skip_bytes;    // u8  [B][n4z][n4y][n4x] skip level (0 = block holds a valid sample cell)
+    int wpr;                        // 32-cell words per x row of the cell-class bitmask
+    size_t vbit_off, vbit_bytes;    // uint2 [B][Dz][Dy][wpr], bit x of (.x,.y): 00 invalid sample cell, 10 valid with all
+                                    // 8 corners > 0, 01 valid with all 8 corners < 0, 11 valid, mixed signs
     size_t list_off, list_bytes;    // backward: int32 counter (256 B) + int2 (voxel, chunk) list
-    size_t loss_off, loss_bytes;    // double[8] loss accumulators
+    size_t loss_off, loss_bytes;    // double[kLossSlots][8] loss accumulators
     size_t hits_off, hits_bytes;    // optional int32 per-pixel hit voxel
     size_t total;
 };
@@ -75,11 +106,15 @@ Layout make_layout(const spsg_raycast_params *p) {
     L.skip_off = off;
     L.skip_bytes = align_up((size_t)p->num_chunks * L.n4x * L.n4y * L.n4z, 256);
     off += L.skip_bytes;
+    L.wpr = (p->dimx + 31) / 32;
+    L.vbit_off = off;
+    L.vbit_bytes = align_up((size_t)p->num_chunks * p->dimz * p->dimy * L.wpr * sizeof(uint2), 256);
+    off += L.vbit_bytes;
     L.list_off = off;
     L.list_bytes = align_up(256 + (size_t)(p->num_locs > 0 ? p->num_locs : 0) * 2 * sizeof(int32_t), 256);
     off += L.list_bytes;
     L.loss_off = off;
-    L.loss_bytes = 256;
+    L.loss_bytes = align_up((size_t)kLossSlots * 8 * sizeof(double), 256);
     off += L.loss_bytes;
     L.hits_off = off;
     L.hits_bytes = align_up((size_t)p->num_chunks * F * p->width * p->height * sizeof(int32_t), 256);
@@ -240,20 +275,26 @@ __device__ __noinline__ bool sample_sdf_exact(const Volume &v, float px, float p
 // absent corner is NaN, which the fma chain propagates: valid <=> dist is not NaN.  (A present voxel holding NaN,
 // or inf * 0, makes the reference's sample "valid with NaN distance", which can never satisfy the sign test
 // and leaves the same march state as an invalid sample -- observationally identical.)
+__device__ __forceinline__ bool frac_guard_ok(float wx, float wy, float wz) {
+    return fminf(wx, fminf(wy, wz)) >= kFracGuard && fmaxf(wx, fmaxf(wy, wz)) <= 1.0f - kFracGuard;
+}
+
+__device__ __forceinline__ float sample_dense(const Volume &v, int ix, int iy, int iz, float wx, float wy, float wz) {
+    const float *__restrict__ b = v.dense + ((size_t)iz * v.dimy + iy) * v.dimx + ix;
+    const int sy = v.dimx, sz = v.dimx * v.dimy;
+    const float v000 = __ldg(b), v100 = __ldg(b + 1), v010 = __ldg(b + sy), v110 = __ldg(b + sy + 1);
+    const float v001 = __ldg(b + sz), v101 = __ldg(b + sz + 1), v011 = __ldg(b + sz + sy), v111 = __ldg(b + sz + sy + 1);
+    return trilerp(wx, wy, wz, v000, v100, v010, v001, v110, v011, v101, v111);
+}
+
 __device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float px, float py, float pz, float &dist) {
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = __fadd_rn(px, -fx), wy = __fadd_rn(py, -fy), wz = __fadd_rn(pz, -fz);
     const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
-    const float wmin = fminf(wx, fminf(wy, wz)), wmax = fmaxf(wx, fmaxf(wy, wz));
-    const bool fast = fast_ok && wmin >= kFracGuard && wmax <= 1.0f - kFracGuard && (ix | iy | iz) >= 0 &&
-                      ix + 1 < v.dimx && iy + 1 < v.dimy && iz + 1 < v.dimz;
+    const bool fast = fast_ok && frac_guard_ok(wx, wy, wz) && (ix | iy | iz) >= 0 && ix + 1 < v.dimx &&
+                      iy + 1 < v.dimy && iz + 1 < v.dimz;
     if (fast) {
-        const float *__restrict__ b = v.dense + ((size_t)iz * v.dimy + iy) * v.dimx + ix;
-        const int sy = v.dimx, sz = v.dimx * v.dimy;
-        const float v000 = __ldg(b), v100 = __ldg(b + 1), v010 = __ldg(b + sy), v110 = __ldg(b + sy + 1);
-        const float v001 = __ldg(b + sz), v101 = __ldg(b + sz + 1), v011 = __ldg(b + sz + sy),
-                    v111 = __ldg(b + sz + sy + 1);
-        dist = trilerp(wx, wy, wz, v000, v100, v010, v001, v110, v011, v101, v111);
+        dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
         return dist == dist;
     }
     return sample_sdf_exact(v, px, py, pz, dist);
@@ -263,14 +304,14 @@ __device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float 
 // index + dense brick + skip hierarchy
 // ---------------------------------------------------------------------------------------------
 
-// construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + dense SDF scatter + fine occupancy marks +
-// voxel->pixel counter reset, one pass over locs.
+// construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + dense SDF scatter + voxel->pixel counter reset,
+// one pass over locs.
 template <bool kWriteIndex>
 __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict__ locs, long long n,
                                                     int32_t *__restrict__ sparse_mapping,
                                                     const float *__restrict__ vals_sdf, float *__restrict__ dense,
-                                                    uint8_t *__restrict__ skip, int32_t *__restrict__ num, int views,
-                                                    int dimz, int dimy, int dimx, int n4z, int n4y, int n4x) {
+                                                    int32_t *__restrict__ num, int views, int dimz, int dimy,
+                                                    int dimx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const longlong4 l = locs[i];  // (z, y, x, chunk)
@@ -278,16 +319,75 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
     const long long cell = ((b * dimz + z) * dimy + y) * dimx + x;
     if (kWriteIndex) sparse_mapping[cell] = (int32_t)i;
     if (dense) dense[cell] = __ldg(vals_sdf + i);
-    if (skip) {
-        uint8_t *m = skip + ((b * n4z + (z >> kFineLog2)) * n4y + (y >> kFineLog2)) * n4x + (x >> kFineLog2);
-        if (*reinterpret_cast<volatile uint8_t *>(m) == 0) *m = 1;  // benign race: everybody writes 1
-    }
     if (num)
         for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
 }
 
-// Turns the fine occupancy marks (1 = some voxel of this 4^3 block is present) into skip levels, in place:
-//   0 = occupied; k >= 1 = the aligned block of edge 2^(k+1) voxels (4, 8, 16, 32) around it is empty.
+// Cell classes.  For the cell c = (x, y, z) look at the 8 voxels (x..x+1, y..y+1, z..z+1), the corners of every
+// sample whose corner (0,0,0) is c (kernel.cu:131-153):
+//   invalid  some corner absent or outside the grid: such a sample is invalid;
+//   positive all present and in (kTiny, kHuge): the sample is valid and its trilinear value is > 0 -- every weight is
+//            >= 0, they sum to ~1 so one is >= 1/8, and products with values above kTiny cannot underflow;
+//   negative likewise with all corners in (-kHuge, -kTiny): value < 0;
+//   mixed    all present, anything else: the value has to be computed.
+// Encoded in two bit planes per 32 cells of an x row (see Layout).  One warp per 32 cells; also marks every 4^3
+// block that holds at least one valid cell.
+constexpr float kTiny = 1e-30f, kHuge = 3e38f;
+
+__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
+                                                         uint8_t *__restrict__ skip, int num_chunks, int dimz, int dimy,
+                                                         int dimx, int wpr, int n4z, int n4y, int n4x) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long rows = (long long)num_chunks * dimz * dimy;
+    if (warp >= rows * wpr) return;
+    const int xw = (int)(warp % wpr);
+    long long row = warp / wpr;
+    const int y = (int)(row % dimy); row /= dimy;
+    const int z = (int)(row % dimz);
+    const int chunk = (int)(row / dimz);
+    const float *__restrict__ base = dense + (size_t)chunk * dimz * dimy * dimx;
+    const bool inner = (y + 1 < dimy) && (z + 1 < dimz);  // warp-uniform
+    // per x column (x, y..y+1, z..z+1): all present / all positive class / all negative class
+    bool col = false, pos = false, neg = false, coln = false, posn = false, negn = false;
+    if (inner) {
+        const size_t o00 = ((size_t)z * dimy + y) * dimx, o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx,
+                     o11 = o01 + dimx;
+        const int x = xw * 32 + lane;
+        if (x < dimx) {
+            const float a = __ldg(base + o00 + x), b = __ldg(base + o10 + x), c = __ldg(base + o01 + x),
+                        d = __ldg(base + o11 + x);
+            col = (a == a) && (b == b) && (c == c) && (d == d);
+            const float lo = fminf(fminf(a, b), fminf(c, d)), hi = fmaxf(fmaxf(a, b), fmaxf(c, d));
+            pos = col && lo > kTiny && hi < kHuge;
+            neg = col && hi < -kTiny && lo > -kHuge;
+        }
+        const int xn = xw * 32 + 32;
+        if (lane == 0 && xn < dimx) {
+            const float a = __ldg(base + o00 + xn), b = __ldg(base + o10 + xn), c = __ldg(base + o01 + xn),
+                        d = __ldg(base + o11 + xn);
+            coln = (a == a) && (b == b) && (c == c) && (d == d);
+            const float lo = fminf(fminf(a, b), fminf(c, d)), hi = fmaxf(fmaxf(a, b), fmaxf(c, d));
+            posn = coln && lo > kTiny && hi < kHuge;
+            negn = coln && hi < -kTiny && lo > -kHuge;
+        }
+    }
+#define SPSG_PAIR(m, mn) ((m) & (((m) >> 1) | (((mn) & 1u) << 31)))
+    const unsigned cb = __ballot_sync(0xffffffffu, col), cbn = __ballot_sync(0xffffffffu, coln);
+    const unsigned pb = __ballot_sync(0xffffffffu, pos), pbn = __ballot_sync(0xffffffffu, posn);
+    const unsigned nb = __ballot_sync(0xffffffffu, neg), nbn = __ballot_sync(0xffffffffu, negn);
+    const unsigned v = SPSG_PAIR(cb, cbn), vp = SPSG_PAIR(pb, pbn), vn = SPSG_PAIR(nb, nbn);
+#undef SPSG_PAIR
+    if (lane == 0) vbits[warp] = make_uint2(v & ~vn, v & ~vp);
+    if (lane < 8 && ((v >> (4 * lane)) & 0xfu)) {
+        const int bx = xw * 8 + lane;
+        uint8_t *m = skip + (((size_t)chunk * n4z + (z >> kFineLog2)) * n4y + (y >> kFineLog2)) * n4x + bx;
+        if (*reinterpret_cast<volatile uint8_t *>(m) == 0) *m = 1;  // benign race: everybody writes 1
+    }
+}
+
+// Turns the block marks (1 = some sample cell of this 4^3 block is valid) into skip levels, in place:
+//   0 = marked; k >= 1 = the aligned block of edge 2^(k+1) voxels (4, 8, 16, 32) around it has no valid sample cell.
 // One CTA per 32^3-voxel super block (8^3 fine blocks).
 __global__ void __launch_bounds__(512) skip_hierarchy_kernel(uint8_t *__restrict__ skip, int n4z, int n4y, int n4x,
                                                              int sbz, int sby, int sbx) {
@@ -346,6 +446,8 @@ struct ForwardArgs {
     int32_t *mapping3dto2d, *mapping3dto2d_num;
     const float *dense;
     const uint8_t *skip;
+    const uint2 *vbits;
+    int wpr;
     int32_t *hits;
     int width, height;
     float depth_min, depth_max, thresh, inc;
@@ -367,22 +469,25 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Cooperative write-out of one channel group of the CTA tile: smem [kTileH][kTileW*C] -> global rows.
+constexpr int kWarpW = 8, kWarpH = 4;  // pixels per warp
+
+// Write-out of one channel group of a warp's 8x4 pixel tile: smem [kWarpH][kWarpW*C] -> global rows, by the warp.
 template <int C>
-__device__ __forceinline__ void store_tile(const float *__restrict__ s, float *__restrict__ g, int img, int x0, int y0,
-                                           int width, int height, bool vec) {
-    const int rows = min(kTileH, height - y0), cols = min(kTileW, width - x0);
-    constexpr int kRow = kTileW * C;
-    if (vec && cols == kTileW) {
+__device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, float *__restrict__ g, int img, int x0,
+                                                int y0, int width, int height, bool vec, int lane) {
+    const int rows = min(kWarpH, height - y0), cols = min(kWarpW, width - x0);
+    constexpr int kRow = kWarpW * C;
+    if (rows <= 0 || cols <= 0) return;
+    if (vec && cols == kWarpW) {
         constexpr int kVecRow = kRow / 4;
-        for (int e = threadIdx.x; e < rows * kVecRow; e += kTilePix) {
+        for (int e = lane; e < rows * kVecRow; e += 32) {
             const int r = e / kVecRow, k = e - r * kVecRow;
             float4 *dst = reinterpret_cast<float4 *>(g + ((size_t)(img * height + y0 + r) * width + x0) * C) + k;
             __stcs(dst, reinterpret_cast<const float4 *>(s + r * kRow)[k]);
         }
     } else {
         const int n = cols * C;
-        for (int e = threadIdx.x; e < rows * kRow; e += kTilePix) {
+        for (int e = lane; e < rows * kRow; e += 32) {
             const int r = e / kRow, k = e - r * kRow;
             if (k < n) __stcs(g + ((size_t)(img * height + y0 + r) * width + x0) * C + k, s[r * kRow + k]);
         }
@@ -393,12 +498,12 @@ __device__ __forceinline__ void store_tile(const float *__restrict__ s, float *_
 // :215-249 (hit write-out + voxel->pixel registration); kLoss adds the 2D losses (train.py:635-638,
 // loss.py:246-257, train.py:744-746) to the epilogue.
 template <bool kLoss>
-__global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const ForwardArgs a) {
-    __shared__ __align__(16) float s_sem[kTilePix * 14];
-    __shared__ __align__(16) float s_col[kTilePix * 3];
-    __shared__ __align__(16) float s_nrm[kTilePix * 3];
-    __shared__ __align__(16) float s_dep[kTilePix];
-    __shared__ float s_red[4][6];
+__global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const ForwardArgs a) {
+    // per-warp staging of the rendered tile: the kernel has no block-wide barrier, warps retire independently
+    __shared__ __align__(16) float s_sem_all[kTilePix * 14];
+    __shared__ __align__(16) float s_col_all[kTilePix * 3];
+    __shared__ __align__(16) float s_nrm_all[kTilePix * 3];
+    __shared__ __align__(16) float s_dep_all[kTilePix];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
@@ -413,9 +518,11 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
     int hit = -1;
     float depth = 0.0f;
 
-    if (active) {
-        const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, ux, uy, a.depth_min,
-                                a.depth_max);
+    {
+        // Lanes outside the image run the same warp-synchronous loops below with an exhausted ray.
+        const int img_c = img;
+        const Ray r = setup_ray(a.view_matrix + (size_t)img_c * 16, a.intrinsics + (size_t)img_c * 4,
+                                active ? ux : 0u, active ? uy : 0u, a.depth_min, a.depth_max);
         const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
         Volume v;
         v.index = a.sparse_mapping + (size_t)chunk * cells;
@@ -423,6 +530,7 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
         v.dense = a.dense + (size_t)chunk * cells;
         v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
         const uint8_t *__restrict__ skipmap = a.skip + (size_t)chunk * a.n4z * a.n4y * a.n4x;
+        const uint2 *__restrict__ vbits = a.vbits + (size_t)chunk * a.dimz * a.dimy * a.wpr;
         const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
         const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
         const bool fast_ok = max(a.dimx, max(a.dimy, a.dimz)) <= kMaxFastDim;
@@ -433,8 +541,8 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
         Stepper step;
         step.init(a.inc);
 
-        float ray = r.t0, t_end = r.t1;
-        if (clip) {
+        float ray = r.t0, t_end = active ? r.t1 : -kInf;
+        if (clip && active) {
             // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
             float tin = -kInf, tout = kInf;
 #define SPSG_SLAB(o, d, inv, lo, hi)                                        \
@@ -452,7 +560,7 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
 #undef SPSG_SLAB
             const float margin = 0.0625f;
             if (!(tin <= tout)) {
-                t_end = ray;  // misses the grid: nothing to march
+                t_end = -kInf;  // misses the grid: nothing to march
             } else {
                 t_end = fminf(t_end, tout + margin);
                 // jump to (at most) the last sample before tin - margin
@@ -463,98 +571,165 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
             }
         }
 
+        // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the sign the
+        // cell class guarantees; the value is computed if and when a crossing needs it.
         float last_sdf = 0.0f, last_alpha = 0.0f;
-        bool last_ok = false;
+        bool last_ok = false, last_lazy = false;
 
-        for (;;) {  // march to a sign change, refine it, repeat if the refinement is rejected
-            bool crossing = false;
-            float dist = 0.0f;
-            for (;;) {
-                // ---- skip phase: advance to the next sample that has to be evaluated
-                bool cand = false;
-                float px = 0.0f, py = 0.0f, pz = 0.0f;
-                while (ray < t_end && !cand) {  // kernel.cu:200
-                    px = __fmaf_rn(r.dx, ray, r.camx);
-                    py = __fmaf_rn(r.dy, ray, r.camy);
-                    pz = __fmaf_rn(r.dz, ray, r.camz);
-                    cand = true;
-                    if (skip) {
-                        const int ix = __float2int_rd(px), iy = __float2int_rd(py), iz = __float2int_rd(pz);
-                        if ((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
-                            (unsigned)iz < (unsigned)a.dimz) {
-                            const int level = skipmap[((iz >> kFineLog2) * a.n4y + (iy >> kFineLog2)) * a.n4x +
-                                                      (ix >> kFineLog2)];
-                            if (level != 0) {
-                                // p is inside an empty aligned block of edge `size`.  If it is at least kBoxEps inside
-                                // on every axis, the sample's corner (0,0,0) lies in the block and is absent: the sample
-                                // is invalid (kernel.cu:131,259) and so is every later one up to the block's exit.
-                                const int size = 2 << level, mask = ~(size - 1);
-                                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
-                                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
-                                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
-                                if (px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz) {
-                                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
-                                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
-                                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
-                                    const float tout = fminf(tx_, fminf(ty_, tz_));
-                                    int want = 1;
-                                    if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
-                                    last_ok = false;  // kernel.cu:259
-                                    ray = step.advance(ray, want);
-                                    cand = false;
-                                }
-                            }
-                        }
+        // Per-sample state machine.  Every sample of the reference's march is in exactly one state:
+        //   kJump   inside an aligned block without valid cells: invalid, and so is everything up to the block's exit
+        //   kStep   invalid cell, or valid cell whose sign is known and does not cross: nothing to compute
+        //   kEval   the trilinear value is needed (mixed-sign cell or possible crossing); kEvalExact: edge case that
+        //           has to go through the reference's exact corner arithmetic
+        //   kCross  sign change found, waiting for the warp's refinement round;  kDone: ray exhausted or pixel hit
+        // The loops below are warp-synchronous (every lane of the warp takes part in every __any_sync): each state is
+        // served by its own inner loop, so lanes in the same state execute together instead of taking turns.
+        enum { kJump = 0, kStep = 1, kEval = 2, kEvalExact = 3, kCross = 4, kDone = 5 };
+        const unsigned kFull = 0xffffffffu;
+        float px = 0.0f, py = 0.0f, pz = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f, dist = 0.0f;
+        int ix = 0, iy = 0, iz = 0, level = 0;
+        float step_sign = 0.0f;  // kStep: 0 = invalid cell, +-1 = valid cell with that sign
+        auto classify = [&]() -> int {
+            if (!(ray < t_end)) return kDone;  // kernel.cu:200
+            px = __fmaf_rn(r.dx, ray, r.camx);
+            py = __fmaf_rn(r.dy, ray, r.camy);
+            pz = __fmaf_rn(r.dz, ray, r.camz);
+            if (!skip) return kEvalExact;
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            ix = __float2int_rz(fx); iy = __float2int_rz(fy); iz = __float2int_rz(fz);
+            if (!((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy && (unsigned)iz < (unsigned)a.dimz))
+                return kEvalExact;
+            level = skipmap[((iz >> kFineLog2) * a.n4y + (iy >> kFineLog2)) * a.n4x + (ix >> kFineLog2)];
+            if (level != 0) return kJump;
+            if (!fast_ok) return kEvalExact;
+            // Block with valid cells: decide this sample by its own cell.  With frac(p) clear of the cell faces the
+            // reference's corners are exactly floor(p) + {0,1}, and the cell's class bits say whether all 8 are present
+            // and whether they share a sign.
+            wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
+            if (!frac_guard_ok(wx, wy, wz)) return kEvalExact;
+            const uint2 word = __ldg(vbits + ((size_t)iz * a.dimy + iy) * a.wpr + (ix >> 5));
+            const unsigned ca = (word.x >> (ix & 31)) & 1u, cb = (word.y >> (ix & 31)) & 1u;
+            if ((ca | cb) == 0u) { step_sign = 0.0f; return kStep; }
+            if ((ca & cb) != 0u) return kEval;
+            step_sign = ca ? 1.0f : -1.0f;
+            // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN: it came from a valid, non-NaN sample)
+            return (last_ok && __fmul_rn(last_sdf, step_sign) < 0.0f) ? kEval : kStep;
+        };
+
+        int state = classify();
+        for (;;) {
+            if (!__any_sync(kFull, state <= kEvalExact)) {
+                // ---- refinement round: every lane is either waiting with a crossing or finished
+                if (!__any_sync(kFull, state == kCross)) break;
+                if (state == kCross) {
+                    if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
+                        float dl = last_sdf;
+                        if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
+                                       __fmaf_rn(r.dz, last_alpha, r.camz), dl))
+                            last_sdf = dl;
+                        last_lazy = false;
                     }
-                }
-                if (!cand) break;  // ray exhausted
-                // ---- sample phase (converged across the warp)
-                if (sample_sdf(v, fast_ok, px, py, pz, dist)) {
-                    if (last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
-                        crossing = true;
-                        break;
-                    }
-                    last_sdf = dist; last_alpha = ray; last_ok = true;  // :254-256
-                } else {
-                    last_ok = false;  // :259
-                }
-                ray = __fadd_rn(ray, a.inc);  // :257,:260
-            }
-            if (!crossing) break;  // miss
-            // ---- findIntersectionBisection (:166-187), executed once the warp has converged here
-            float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
-            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-            bool ok = true;
+                    // findIntersectionBisection (:166-187)
+                    float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
+                    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+                    bool ok = true;
 #pragma unroll 1
-            for (int k = 0; k < 3; k++) {
-                c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
-                cx = __fmaf_rn(r.dx, c, r.camx);
-                cy = __fmaf_rn(r.dy, c, r.camy);
-                cz = __fmaf_rn(r.dz, c, r.camz);
-                float dc;
-                if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
-                    ok = false;
-                    break;
+                    for (int k = 0; k < 3; k++) {
+                        c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
+                        cx = __fmaf_rn(r.dx, c, r.camx);
+                        cy = __fmaf_rn(r.dy, c, r.camy);
+                        cz = __fmaf_rn(r.dz, c, r.camz);
+                        float dc;
+                        if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
+                            ok = false;
+                            break;
+                        }
+                        if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+                    }
+                    if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
+                        depth = __fdiv_rn(c, r.d2r);                                                     // :215
+                        // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel
+                        // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
+                        // ever says otherwise the reference reads stale registers -- we keep marching instead.
+                        const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
+                        hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
+                    }
+                    if (hit >= 0) {
+                        state = kDone;
+                    } else {
+                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                        ray = __fadd_rn(ray, a.inc);                                           // :257
+                        state = classify();
+                    }
                 }
-                if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+                continue;
             }
-            if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
-                depth = __fdiv_rn(c, r.d2r);                                                     // :215
-                // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel round(cam + alpha*dir)
-                // (:241-242, same fma).  It is one of the 8 present corners; if rounding ever says otherwise the
-                // reference reads stale registers -- we render the pixel with a zero payload instead.
-                const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
-                hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
-                if (hit >= 0) break;
+            // ---- jump phase
+            while (__any_sync(kFull, state == kJump)) {
+                if (state == kJump) {
+                    // p is inside an aligned block of edge `size` without any valid sample cell.  If it is at least
+                    // kBoxEps inside on every axis, the sample's corner (0,0,0) lies in the block: the sample is invalid
+                    // (kernel.cu:131,259) and so is every later one up to the block's exit.
+                    const int size = 2 << level, mask = ~(size - 1);
+                    const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
+                    const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
+                    const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
+                    if (!(px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz)) {
+                        state = kEvalExact;  // within kBoxEps of the block's faces: let the exact path decide
+                    } else {
+                        const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
+                        const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
+                        const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
+                        const float tout = fminf(tx_, fminf(ty_, tz_));
+                        int want = 1;
+                        if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
+                        last_ok = false;  // kernel.cu:259
+                        ray = step.advance(ray, want);
+                        state = classify();
+                    }
+                }
             }
-            last_sdf = dist; last_alpha = ray; last_ok = true;  // :254-256
-            ray = __fadd_rn(ray, a.inc);                        // :257
+            // ---- step phase
+            while (__any_sync(kFull, state == kStep)) {
+                if (state == kStep) {
+                    if (step_sign == 0.0f) {
+                        last_ok = false;  // kernel.cu:259
+                    } else {
+                        last_sdf = step_sign; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
+                    }
+                    ray = __fadd_rn(ray, a.inc);  // :257,:260
+                    state = classify();
+                }
+            }
+            // ---- eval phase: one sample per lane that needs a value
+            if (state == kEval || state == kEvalExact) {
+                bool valid;
+                if (state == kEval) {
+                    dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
+                    valid = dist == dist;
+                } else {
+                    valid = sample_sdf(v, fast_ok, px, py, pz, dist);
+                }
+                if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
+                    state = kCross;
+                } else {
+                    if (valid) {
+                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                    } else {
+                        last_ok = false;  // :259
+                    }
+                    ray = __fadd_rn(ray, a.inc);  // :257,:260
+                    state = classify();
+                }
+            }
         }
     }
 
     // ---- write-out (kernel.cu:276-285 init, :217-239 hit) through shared memory
     const float ninf = __int_as_float(0xff800000);
-    const int tp = ty * kTileW + tx;
+    const int tp = lane;  // pixel index inside the warp's 8x4 tile (row-major)
+    float *s_sem = s_sem_all + warp * 32 * 14, *s_col = s_col_all + warp * 32 * 3, *s_nrm = s_nrm_all + warp * 32 * 3,
+          *s_dep = s_dep_all + warp * 32;
     float col0 = ninf, col1 = ninf, col2 = ninf, dep = ninf;
     float sem[14];
 #pragma unroll
@@ -617,33 +792,38 @@ __global__ void __launch_bounds__(kTilePix) raycast_forward_kernel(const Forward
                 }
             }
         }
+        float mine = 0.0f;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            acc[k] = warp_sum(acc[k]);
-            if (lane == 0) s_red[warp][k] = acc[k];
+            const float t = warp_sum(acc[k]);
+            if (lane == k) mine = t;
         }
+        // one double atomic per warp and term, spread over kLossSlots copies of the accumulators
+        const unsigned slot = (blockIdx.x * 4u + blockIdx.y * 37u + blockIdx.z * 11u + warp) % kLossSlots;
+        if (lane < 6 && mine != 0.0f) atomicAdd(a.loss.accum + slot * 8 + lane, (double)mine);
     }
-    __syncthreads();
-    if (kLoss && threadIdx.x < 6) {
-        const float t = s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
-        if (t != 0.0f) atomicAdd(a.loss.accum + threadIdx.x, (double)t);
-    }
+    __syncwarp();
     const bool vec = a.vec_ok != 0;
-    store_tile<14>(s_sem, a.image_semantic, img, x0, y0, a.width, a.height, vec);
-    store_tile<3>(s_col, a.image_color, img, x0, y0, a.width, a.height, vec);
-    store_tile<3>(s_nrm, a.image_normal, img, x0, y0, a.width, a.height, vec);
-    store_tile<1>(s_dep, a.image_depth, img, x0, y0, a.width, a.height, vec);
+    const int wx0 = x0 + (warp & 1) * kWarpW, wy0 = y0 + (warp >> 1) * kWarpH;
+    store_warp_tile<14>(s_sem, a.image_semantic, img, wx0, wy0, a.width, a.height, vec, lane);
+    store_warp_tile<3>(s_col, a.image_color, img, wx0, wy0, a.width, a.height, vec, lane);
+    store_warp_tile<3>(s_nrm, a.image_normal, img, wx0, wy0, a.width, a.height, vec, lane);
+    store_warp_tile<1>(s_dep, a.image_depth, img, wx0, wy0, a.width, a.height, vec, lane);
 }
+
 
 // loss_out[0..3] = depth, colour, semantic, weighted total; [4..6] = normalisers the backward needs.
 __global__ void finalize_loss_kernel(const double *__restrict__ acc, float *__restrict__ out, float w_depth,
                                      float w_color, float w_sem, int has_depth, int has_color, int has_sem) {
-    const float ld = has_depth ? (float)(acc[0] / acc[1]) : 0.0f;  // mean over an empty set is NaN, like torch.mean
-    const float lc = has_color ? (float)(acc[2] / acc[3]) : 0.0f;
-    const float ls = has_sem ? (float)(acc[4] / acc[5]) : 0.0f;
+    double t[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < kLossSlots; s++)
+        for (int k = 0; k < 6; k++) t[k] += acc[s * 8 + k];
+    const float ld = has_depth ? (float)(t[0] / t[1]) : 0.0f;  // mean over an empty set is NaN, like torch.mean
+    const float lc = has_color ? (float)(t[2] / t[3]) : 0.0f;
+    const float ls = has_sem ? (float)(t[4] / t[5]) : 0.0f;
     out[0] = ld; out[1] = lc; out[2] = ls;
     out[3] = w_depth * ld + w_color * lc + w_sem * ls;
-    out[4] = (float)acc[1]; out[5] = (float)acc[3]; out[6] = (float)acc[5];
+    out[4] = (float)t[1]; out[5] = (float)t[3]; out[6] = (float)t[5];
     out[7] = 0.0f;
 }
 
@@ -699,21 +879,33 @@ __global__ void __launch_bounds__(256) backward_scan_kernel(const BackwardArgs a
 }
 
 // Upstream gradient of one pixel for this lane's channel.  Lanes 0-13 semantic, 16-18 colour, 19 depth,
-// 20-22 normal; other lanes idle.
+// 20-22 normal; other lanes idle.  Plain variant: one load from this lane's image (base pointer + per-pixel stride
+// prepared by lane_source).  Fused variant: recomputed from the rendering and the targets.
+struct LaneSource {
+    const float *base;  // nullptr: idle lane
+    unsigned stride;
+};
+
+__device__ __forceinline__ LaneSource lane_source(const BackwardArgs &a, int lane) {
+    LaneSource s;
+    s.base = nullptr; s.stride = 0;
+    if (lane < 14) { s.base = a.grad_semantic + lane; s.stride = 14; }
+    else if (lane >= 16 && lane < 19) { s.base = a.grad_color + (lane - 16); s.stride = 3; }
+    else if (lane == 19) { s.base = a.grad_depth; s.stride = 1; }
+    else if (lane >= 20 && lane < 23) { s.base = a.grad_normal + (lane - 20); s.stride = 3; }
+    return s;
+}
+
 template <bool kFused>
-__device__ __forceinline__ float pixel_grad(const BackwardArgs &a, int lane, size_t gpix) {
+__device__ __forceinline__ float pixel_grad(const BackwardArgs &a, const LaneSource &src, int lane, unsigned gpix) {
     if (!kFused) {
-        if (lane < 14) return __ldg(a.grad_semantic + gpix * 14 + lane);
-        if (lane >= 16 && lane < 19) return __ldg(a.grad_color + gpix * 3 + (lane - 16));
-        if (lane == 19) return __ldg(a.grad_depth + gpix);
-        if (lane >= 20 && lane < 23) return __ldg(a.grad_normal + gpix * 3 + (lane - 20));
-        return 0.0f;
+        return src.base ? __ldg(src.base + (size_t)gpix * src.stride) : 0.0f;
     } else {
         const LossArgs &L = a.loss;
         float g = 0.0f;
         // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
         const int y = L.target_label ? (int)L.target_label[gpix] : 14;
-        float logit = (lane < 14) ? __ldg(a.image_semantic + gpix * 14 + lane) : -CUDART_INF_F;
+        float logit = (lane < 14) ? __ldg(a.image_semantic + (size_t)gpix * 14 + lane) : -CUDART_INF_F;
         if (y < 14 && __shfl_sync(0xffffffffu, logit, 0) != -CUDART_INF_F) {  // warp-uniform: one pixel per iteration
             float m = logit;
 #pragma unroll
@@ -729,8 +921,8 @@ __device__ __forceinline__ float pixel_grad(const BackwardArgs &a, int lane, siz
         }
         if (lane >= 16 && lane < 19 && L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
             const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
-            const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + gpix * 3 + (lane - 16)), w),
-                                      -__fmul_rn(__ldg(L.target_color + gpix * 3 + (lane - 16)), w));
+            const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + (size_t)gpix * 3 + (lane - 16)), w),
+                                      -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + (lane - 16)), w));
             g = a.w_color * ((d > 0.0f) - (d < 0.0f)) * w / a.loss_out[5];
         }
         if (lane == 19 && L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
@@ -744,44 +936,67 @@ __device__ __forceinline__ float pixel_grad(const BackwardArgs &a, int lane, siz
     }
 }
 
-// Pass 2: one warp per hit voxel, lane == channel.  For every view the warp walks the voxel's registered pixels
-// in registration order and accumulates grad/cnt (kernel.cu:398-418) -- a fixed order, hence deterministic.
+// Pass 2: one warp per hit voxel, lane == channel.  The warp first fetches the voxel's per-view counters in one
+// round trip (lane == view), then the registered pixel ids of all views in a second one (flattened view-major
+// list, lane == list position), and finally streams the pixels' gradients eight at a time, accumulating grad/cnt
+// (kernel.cu:398-418) in list order -- a fixed order, hence deterministic.
 template <bool kFused>
 __global__ void __launch_bounds__(256) backward_gather_kernel(const BackwardArgs a) {
+    const unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
     const int count = *a.list_count;
-    const size_t P = (size_t)a.width * a.height;
+    const unsigned P = (unsigned)(a.width * a.height);
+    const LaneSource src = lane_source(a, lane);
     for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < count; item += warps_total) {
         const int2 e = a.list[item];
         const int vidx = e.x, chunk = e.y;
         float acc = 0.0f;
-        for (int f = 0; f < a.views; f++) {
-            const size_t row = (size_t)f * a.num_locs + vidx;
-            const int num = __ldg(a.mapping3dto2d_num + row);
-            if (num <= 0) continue;
-            const int cnt = min(num, a.max_pixels);
-            const float fcnt = (float)cnt;
-            const size_t img_base = ((size_t)chunk * a.views + f) * P;
-            float sum = 0.0f;
-            for (int t0 = 0; t0 < cnt; t0 += 32) {
-                const int my_pix = (t0 + lane < cnt) ? __ldg(a.mapping3dto2d + row * a.max_pixels + t0 + lane) : 0;
-                const int m = min(32, cnt - t0);
-                int t = 0;
-                for (; t + 4 <= m; t += 4) {  // 4 independent gathers in flight, summed in order
-                    const float g0 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t));
-                    const float g1 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 1));
-                    const float g2 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 2));
-                    const float g3 = pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t + 3));
-                    sum = __fadd_rn(sum, __fdiv_rn(g0, fcnt));
-                    sum = __fadd_rn(sum, __fdiv_rn(g1, fcnt));
-                    sum = __fadd_rn(sum, __fdiv_rn(g2, fcnt));
-                    sum = __fadd_rn(sum, __fdiv_rn(g3, fcnt));
-                }
-                for (; t < m; t++)
-                    sum = __fadd_rn(sum, __fdiv_rn(pixel_grad<kFused>(a, lane, img_base + __shfl_sync(0xffffffffu, my_pix, t)), fcnt));
+        for (int f0 = 0; f0 < a.views; f0 += 32) {  // views in groups of 32 (one per lane)
+            const int f = f0 + lane;
+            int cnt = 0;
+            if (f < a.views) cnt = min(max(__ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + vidx), 0), a.max_pixels);
+            // exclusive prefix sum of the counts over lanes
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
             }
-            acc += sum;
+            const int excl = incl - cnt;
+            const int total = __shfl_sync(kFull, incl, 31);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                // list position t0 + lane -> (view, slot): the view whose [excl, incl) range holds it
+                const int pos = t0 + lane;
+                int my_view = 0, my_excl = 0, my_cnt = 1;
+                for (int k = 0; k < min(32, a.views - f0); k++) {
+                    const int ek = __shfl_sync(kFull, excl, k), ck = __shfl_sync(kFull, cnt, k);
+                    if (pos >= ek && pos < ek + ck) { my_view = k; my_excl = ek; my_cnt = ck; }
+                }
+                unsigned my_pix = 0;  // global pixel index; < 2^32 / 14 (check_params)
+                if (pos < total) {
+                    const size_t row = (size_t)(f0 + my_view) * a.num_locs + vidx;
+                    my_pix = (unsigned)(chunk * a.views + f0 + my_view) * P +
+                             (unsigned)__ldg(a.mapping3dto2d + row * a.max_pixels + (pos - my_excl));
+                }
+                const float my_fcnt = __frcp_rn((float)my_cnt);
+                const int m = min(32, total - t0);
+                int t = 0;
+                for (; t + 8 <= m; t += 8) {  // 8 independent gathers in flight, summed in order
+                    float g[8], c[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        g[u] = pixel_grad<kFused>(a, src, lane, __shfl_sync(kFull, my_pix, t + u));
+                        c[u] = __shfl_sync(kFull, my_fcnt, t + u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = __fmaf_rn(g[u], c[u], acc);
+                }
+                for (; t < m; t++) {
+                    const float g = pixel_grad<kFused>(a, src, lane, __shfl_sync(kFull, my_pix, t));
+                    acc = __fmaf_rn(g, __shfl_sync(kFull, my_fcnt, t), acc);
+                }
+            }
         }
         if (lane < 14) a.d_semantic[(size_t)vidx * 14 + lane] = acc;
         else if (lane >= 16 && lane < 19) a.d_color[(size_t)vidx * 3 + (lane - 16)] = acc;
@@ -915,26 +1130,31 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     uint8_t *ws = (uint8_t *)workspace;
     float *dense = (float *)(ws + L.dense_off);
     uint8_t *skip = ws + L.skip_off;
+    uint2 *vbits = (uint2 *)(ws + L.vbit_off);
     double *accum = (double *)(ws + L.loss_off);
     const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
 
     if (build_index) CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));  // kernel.cu:515
     CUDA_TRY(cudaMemsetAsync(dense, 0xff, L.dense_bytes, st));  // 0xffffffff is a NaN: every voxel absent
     CUDA_TRY(cudaMemsetAsync(skip, 0, L.skip_bytes, st));
-    if (targets) CUDA_TRY(cudaMemsetAsync(accum, 0, 8 * sizeof(double), st));
+    if (targets) CUDA_TRY(cudaMemsetAsync(accum, 0, L.loss_bytes, st));
     if (p->num_locs > 0) {
         const unsigned blocks = (unsigned)((p->num_locs + 255) / 256);
         if (build_index)
             index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
-                                                       dense, skip, mapping3dto2d_num, p->views_per_chunk, p->dimz,
-                                                       p->dimy, p->dimx, L.n4z, L.n4y, L.n4x);
+                                                       dense, mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
+                                                       p->dimx);
         else
             index_kernel<false><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
-                                                        dense, skip, mapping3dto2d_num, p->views_per_chunk, p->dimz,
-                                                        p->dimy, p->dimx, L.n4z, L.n4y, L.n4x);
+                                                        dense, mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
+                                                        p->dimx);
         CUDA_TRY(cudaGetLastError());
     }
     {
+        const long long vwarps = (long long)p->num_chunks * p->dimz * p->dimy * L.wpr;
+        cell_class_kernel<<<(unsigned)((vwarps + 7) / 8), 256, 0, st>>>(dense, vbits, skip, p->num_chunks, p->dimz,
+                                                                       p->dimy, p->dimx, L.wpr, L.n4z, L.n4y, L.n4x);
+        CUDA_TRY(cudaGetLastError());
         const int sbx = (L.n4x + kSuper - 1) / kSuper, sby = (L.n4y + kSuper - 1) / kSuper,
                   sbz = (L.n4z + kSuper - 1) / kSuper;
         skip_hierarchy_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(skip, L.n4z, L.n4y, L.n4x,
@@ -949,7 +1169,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_color = image_color; a.image_depth = image_depth; a.image_normal = image_normal;
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
-    a.dense = dense; a.skip = skip;
+    a.dense = dense; a.skip = skip; a.vbits = vbits; a.wpr = L.wpr;
     a.hits = (p->flags & SPSG_FLAG_RECORD_HITS) ? (int32_t *)(ws + L.hits_off) : nullptr;
     a.width = p->width; a.height = p->height;
     a.depth_min = p->depth_min; a.depth_max = p->depth_max; a.thresh = p->thresh_sample_dist; a.inc = p->ray_increment;
@@ -964,12 +1184,16 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     const dim3 grid((p->width + kTileW - 1) / kTileW, (p->height + kTileH - 1) / kTileH,
                     p->num_chunks * p->views_per_chunk);
     if (targets) {
-        raycast_forward_kernel<true><<<grid, kTilePix, 0, st>>>(a);
+        {
+            ScopedKernelTimer timer(0, st);
+            raycast_forward_kernel<true><<<grid, kTilePix, 0, st>>>(a);
+        }
         CUDA_TRY(cudaGetLastError());
         finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
                                               targets->weight_semantic, targets->target_depth != nullptr,
                                               targets->target_color != nullptr, targets->target_label != nullptr);
     } else {
+        ScopedKernelTimer timer(0, st);
         raycast_forward_kernel<false><<<grid, kTilePix, 0, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
@@ -1019,8 +1243,11 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned blocks = (unsigned)(sms * 8);  // 8 resident 256-thread CTAs per SM, grid-stride over the list
-    if (fused) backward_gather_kernel<true><<<blocks, 256, 0, st>>>(a);
-    else backward_gather_kernel<false><<<blocks, 256, 0, st>>>(a);
+    {
+        ScopedKernelTimer timer(1, st);
+        if (fused) backward_gather_kernel<true><<<blocks, 256, 0, st>>>(a);
+        else backward_gather_kernel<false><<<blocks, 256, 0, st>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }
@@ -1031,6 +1258,32 @@ extern "C" {
 
 const char *spsg_version(void) { return "spsg_raycast_b200 0.2 (sm_100a)"; }
 const char *spsg_last_error(void) { return g_err; }
+
+void spsg_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing = on != 0;
+}
+
+int spsg_timing_read(int which, double *total_ms, int *launches) {
+    if (which < 0 || which > 1 || !total_ms || !launches) return fail(SPSG_ERR_INVALID_ARGUMENT, "bad timing query");
+    std::vector<EventPair> evs;
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        evs.swap(g_ev[which]);
+    }
+    *total_ms = 0.0;
+    *launches = 0;
+    for (EventPair &e : evs) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) {
+            *total_ms += ms;
+            *launches += 1;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    return SPSG_OK;
+}
 
 size_t spsg_workspace_bytes(const spsg_raycast_params *p) {
     if (check_params(p)) return 0;
@@ -1047,8 +1300,7 @@ int spsg_build_index(const int64_t *locs, int64_t num_locs, int32_t *sparse_mapp
     CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));
     if (num_locs > 0) {
         index_kernel<true><<<(unsigned)((num_locs + 255) / 256), 256, 0, st>>>(
-            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, nullptr, nullptr, 0, dimz, dimy, dimx,
-            0, 0, 0);
+            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, nullptr, 0, dimz, dimy, dimx);
         CUDA_TRY(cudaGetLastError());
     }
     return SPSG_OK;

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests import refdriver
+from oracle import ref_driver as refdriver
 from tests.common import bits, count_bit_mismatch, hit_image_from_mapping, scene_tensors, views
 
 pytestmark = pytest.mark.gpu

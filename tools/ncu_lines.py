@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Aggregate an ncu source-page CSV (SASS view) per CUDA source line.
 
-usage: tools/ncu_lines.py <report.ncu-rep> <kernel-substring> [top]
+usage: tools/ncu_lines.py <report.ncu-rep> <kernel-regex-for-ncu> [top] [mangled-substring-for-nvdisasm]
 Line numbers come from `nvdisasm -g` of the library's current cubin, matched to the ncu rows by instruction order,
 so the report must have been captured from the same build."""
 import csv, io, os, re, subprocess, sys, tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+mangled = sys.argv[4] if len(sys.argv) > 4 else kern
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "lib", "libspsg_raycast.so")
 tmp = tempfile.mkdtemp()
@@ -17,7 +18,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=
 lines, cur, infn, inl = [], None, False, ""
 for l in dis.splitlines():
     if l.startswith("\t.section\t.text."):
-        infn = kern in l
+        infn = mangled in l
     if not infn:
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
@@ -27,8 +28,14 @@ for l in dis.splitlines():
         lines.append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
-hdr = rows[hi]; body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+# the CSV holds one table per profiled launch: "Kernel Name",<name> / header / rows ...; take the first whose name matches
+want = sys.argv[5] if len(sys.argv) > 5 else kern
+starts = [i for i, r in enumerate(rows) if len(r) >= 2 and r[0] == "Kernel Name"]
+sel = next(i for i in starts if re.search(want, rows[i][1]))
+end = next((j for j in starts if j > sel), len(rows))
+hi = next(i for i in range(sel, end) if "Source" in rows[i] and "Address" in rows[i])
+hdr = rows[hi]; body = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
+print("kernel:", rows[sel][1][:100])
 iI, iS, iSrc, iT = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source"), hdr.index("Thread Instructions Executed")
 print("sass rows %d, disasm instrs %d" % (len(body), len(lines)))
 agg = {}

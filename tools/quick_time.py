@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from spsg_b200 import synthetic as S
 from spsg_b200.raycast_rgbd import RaycastRGBD
-from tests import refdriver
+from oracle import ref_driver as refdriver
 from tests.common import scene_tensors, views
 
 dev = torch.device("cuda", 0)
