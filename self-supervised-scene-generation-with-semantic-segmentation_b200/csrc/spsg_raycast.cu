@@ -582,8 +582,8 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
         //   kEval   the trilinear value is needed (mixed-sign cell or possible crossing); kEvalExact: edge case that
         //           has to go through the reference's exact corner arithmetic
         //   kCross  sign change found, waiting for the warp's refinement round;  kDone: ray exhausted or pixel hit
-        // The loops below are warp-synchronous (every lane of the warp takes part in every __any_sync): each state is
-        // served by its own inner loop, so lanes in the same state execute together instead of taking turns.
+        // The loop below is warp-synchronous (every lane of the warp takes part in every __any_sync): per iteration each
+        // lane handles one event, all lanes classify their next sample together, and refinements are batched.
         enum { kJump = 0, kStep = 1, kEval = 2, kEvalExact = 3, kCross = 4, kDone = 5 };
         const unsigned kFull = 0xffffffffu;
         float px = 0.0f, py = 0.0f, pz = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f, dist = 0.0f;
@@ -599,7 +599,9 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
             ix = __float2int_rz(fx); iy = __float2int_rz(fy); iz = __float2int_rz(fz);
             if (!((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy && (unsigned)iz < (unsigned)a.dimz))
                 return kEvalExact;
+            // both lookups are issued together (independent addresses): one memory round trip per sample
             level = skipmap[((iz >> kFineLog2) * a.n4y + (iy >> kFineLog2)) * a.n4x + (ix >> kFineLog2)];
+            const uint2 word = __ldg(vbits + ((size_t)iz * a.dimy + iy) * a.wpr + (ix >> 5));
             if (level != 0) return kJump;
             if (!fast_ok) return kEvalExact;
             // Block with valid cells: decide this sample by its own cell.  With frac(p) clear of the cell faces the
@@ -607,7 +609,6 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
             // and whether they share a sign.
             wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
             if (!frac_guard_ok(wx, wy, wz)) return kEvalExact;
-            const uint2 word = __ldg(vbits + ((size_t)iz * a.dimy + iy) * a.wpr + (ix >> 5));
             const unsigned ca = (word.x >> (ix & 31)) & 1u, cb = (word.y >> (ix & 31)) & 1u;
             if ((ca | cb) == 0u) { step_sign = 0.0f; return kStep; }
             if ((ca & cb) != 0u) return kEval;
@@ -664,45 +665,37 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
                 }
                 continue;
             }
-            // ---- jump phase
-            while (__any_sync(kFull, state == kJump)) {
-                if (state == kJump) {
-                    // p is inside an aligned block of edge `size` without any valid sample cell.  If it is at least
-                    // kBoxEps inside on every axis, the sample's corner (0,0,0) lies in the block: the sample is invalid
-                    // (kernel.cu:131,259) and so is every later one up to the block's exit.
-                    const int size = 2 << level, mask = ~(size - 1);
-                    const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
-                    const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
-                    const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
-                    if (!(px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz)) {
-                        state = kEvalExact;  // within kBoxEps of the block's faces: let the exact path decide
-                    } else {
-                        const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
-                        const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
-                        const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
-                        const float tout = fminf(tx_, fminf(ty_, tz_));
-                        int want = 1;
-                        if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
-                        last_ok = false;  // kernel.cu:259
-                        ray = step.advance(ray, want);
-                        state = classify();
-                    }
+            // ---- one event per lane and iteration; the three handlers are warp-uniform blocks of code
+            if (state == kStep) {
+                if (step_sign == 0.0f) {
+                    last_ok = false;  // kernel.cu:259
+                } else {
+                    last_sdf = step_sign; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
                 }
-            }
-            // ---- step phase
-            while (__any_sync(kFull, state == kStep)) {
-                if (state == kStep) {
-                    if (step_sign == 0.0f) {
-                        last_ok = false;  // kernel.cu:259
-                    } else {
-                        last_sdf = step_sign; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
-                    }
-                    ray = __fadd_rn(ray, a.inc);  // :257,:260
+                ray = __fadd_rn(ray, a.inc);  // :257,:260
+                state = classify();
+            } else if (state == kJump) {
+                // p is inside an aligned block of edge `size` without any valid sample cell.  If it is at least
+                // kBoxEps inside on every axis, the sample's corner (0,0,0) lies in the block: the sample is invalid
+                // (kernel.cu:131,259) and so is every later one up to the block's exit.
+                const int size = 2 << level, mask = ~(size - 1);
+                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
+                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
+                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
+                if (!(px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz)) {
+                    state = kEvalExact;  // within kBoxEps of the block's faces: let the exact path decide
+                } else {
+                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
+                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
+                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
+                    const float tout = fminf(tx_, fminf(ty_, tz_));
+                    int want = 1;
+                    if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
+                    last_ok = false;  // kernel.cu:259
+                    ray = step.advance(ray, want);
                     state = classify();
                 }
-            }
-            // ---- eval phase: one sample per lane that needs a value
-            if (state == kEval || state == kEvalExact) {
+            } else if (state == kEval || state == kEvalExact) {
                 bool valid;
                 if (state == kEval) {
                     dist = sample_dense(v, ix, iy, iz, wx, wy, wz);

@@ -28,7 +28,7 @@ def scene(seed, dims=(32, 32, 32)):
     sdf = np.clip(np.minimum(d_sphere, d_floor), -3, 3).astype(np.float32)
     mask = np.abs(sdf) < 3
     locs = np.argwhere(mask).astype(np.int64)
-    locs = np.concatenate([locs, np.zeros((locs.shape[0], 1), np.int64)], 1)
+    locs = np.ascontiguousarray(np.concatenate([locs, np.zeros((locs.shape[0], 1), np.int64)], 1))
     n = locs.shape[0]
     color = (rng.integers(0, 256, (n, 3)) / 255.0).astype(np.float32)
     normal = rng.standard_normal((n, 3)).astype(np.float32)

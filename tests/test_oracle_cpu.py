@@ -164,7 +164,7 @@ def test_golden_vectors_from_reference_extension():
         assert (hit_ref != hit).sum() <= max(2, hit.size // 5000), f
         both = hit_ref & hit
         np.testing.assert_allclose(out["depth"][both], g["depth"][both], rtol=1e-4)
-        same = (out["color"][both] == g["color"][both]).all(-1)
+        same = (out["color"][both] == g["color_img"][both]).all(-1)
         assert same.mean() > 0.999
         d = O.raycast_backward(p, g["g_color"], g["g_depth"], g["g_normal"], g["g_semantic"], sm,
                                out["mapping3dto2d"], out["mapping3dto2d_num"])
