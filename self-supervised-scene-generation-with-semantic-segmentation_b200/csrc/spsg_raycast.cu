@@ -6,22 +6,26 @@
 // mask is spelled with __f*_rn intrinsics so nvcc can neither contract nor re-associate it.
 //
 // Design (not a port): see DESIGN.md.  In short
-//   * the march replays the reference's `ray += inc` running sum bit-exactly but jumps over samples
-//     that are provably invalid (outside the grid, or inside an empty aligned 4/8/16/32-voxel block)
-//     with a closed form of the fp32 recurrence that is exact inside one binade;
-//   * SDF values are gathered from a dense fp32 brick (NaN = absent voxel) built together with the
-//     index, so one sample costs 8 independent loads instead of 16 dependent ones;
-//   * the march is a converged "while-while" loop (skip phase / sample phase) and the regula-falsi
-//     refinement is deferred until the whole warp has found its crossing, to keep SIMT lanes busy;
+//   * the march replays the reference's `ray += inc` running sum bit-exactly but jumps over samples whose
+//     outcome is known without evaluating them: samples outside the grid, samples inside an aligned 4/8/16/32-
+//     voxel region without any valid sample cell ("empty"), and samples inside a region whose valid cells all
+//     have 8 strictly positive (or all strictly negative) corners ("sign-uniform": no crossing can start there);
+//     jumps use a closed form of the fp32 recurrence that is exact inside one binade;
+//   * one byte per 4^3 block (region kind + size, staged in shared memory) and one byte per cell (class of the
+//     cell's 8 corners) answer "does this sample need arithmetic"; SDF values come from a dense fp32 brick
+//     (NaN = absent voxel), so a sample that does need arithmetic costs 8 independent loads, not 16 dependent ones;
+//   * the regula-falsi refinement is deferred until every lane of the warp has found its crossing;
 //   * rendered pixels are staged in shared memory and written with coalesced 128-bit stores;
-//   * the backward is a deterministic per-voxel gather over a compacted list of hit voxels (no float
-//     atomics, no 524288-block launch, no 164 MB memsets), optionally fused with the 2D losses.
+//   * the forward appends every (voxel, view) pair that received a pixel to a list, so the backward is one launch:
+//     a deterministic per-voxel gather over that list (no float atomics for one view per chunk, no 524288-block
+//     launch, no 164 MB memsets), optionally fused with the 2D losses.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -29,13 +33,19 @@
 
 namespace {
 
-constexpr int kFineLog2 = 2;             // finest skip block: 4^3 voxels
+constexpr int kFineLog2 = 2;             // finest region: 4^3 voxels ("block")
 constexpr int kFine = 1 << kFineLog2;
-constexpr int kSuper = 8;                // hierarchy kernel handles 8^3 fine blocks = 32^3 voxels per CTA
-constexpr float kBoxEps = 1.0f / 64.0f;  // shrink of skip boxes; >> every fp32 error term
+constexpr int kSuper = 8;                // hierarchy kernel handles 8^3 blocks = 32^3 voxels per CTA
+constexpr float kBoxEps = 1.0f / 64.0f;  // shrink of skip regions; >> every fp32 error term
 constexpr float kFracGuard = 1.0f / 256.0f;  // fast corner path needs frac(p) in [guard, 1-guard]
 constexpr int kMaxFastDim = 8192;        // fast corner path proven for coordinates < 2^13
 constexpr int kLossSlots = 64;           // copies of the loss accumulators (spreads atomic contention)
+constexpr int kMaxSmemBlockMap = 32768;  // block maps up to this size are staged in shared memory
+
+// block map byte = kind << 3 | level; level k >= 1: the aligned region of edge 2^(k+1) voxels around the block
+enum { kKindSurface = 0, kKindEmpty = 1, kKindPos = 2, kKindNeg = 3 };
+// cell class byte
+enum { kCellInvalid = 0, kCellPos = 1, kCellNeg = 2, kCellMixed = 3 };
 
 thread_local char g_err[512] = "";
 
@@ -79,43 +89,54 @@ struct ScopedKernelTimer {
     }
 };
 
-// Workspace layout (caller-owned scratch, see spsg_workspace_bytes)
+// Workspace layout (caller-owned scratch, see spsg_workspace_bytes).  Written by the forward; the list, and the
+// voxel->pixel tables it indexes, are what the backward of the same call pair reads.
 struct Layout {
-    int n4x, n4y, n4z;  // fine skip blocks per axis
+    int nbx, nby, nbz;              // 4^3 blocks per axis
+    size_t bpc;                     // block-map bytes per chunk (nbx*nby*nbz rounded up to 16)
     size_t dense_off, dense_bytes;  // f32 [B][Dz][Dy][Dx], NaN = absent
-    size_t skip_off, skip_bytes;    // u8  [B][n4z][n4y][n4x] skip level (0 = block holds a valid sample cell)
-    int wpr;                        // 32-cell words per x row of the cell-class bitmask
-    size_t vbit_off, vbit_bytes;    // uint2 [B][Dz][Dy][wpr], bit x of (.x,.y): 00 invalid sample cell, 10 valid with all
-                                    // 8 corners > 0, 01 valid with all 8 corners < 0, 11 valid, mixed signs
-    size_t list_off, list_bytes;    // backward: int32 counter (256 B) + int2 (voxel, chunk) list
+    size_t cmap_off, cmap_bytes;    // u8  [B][Dz][Dy][Dx] class of the sample cell whose corner (0,0,0) is the voxel
+    size_t bmap_off, bmap_bytes;    // u8  [B][bpc] block map
+    size_t zero_off, zero_bytes;    // everything below is cleared by the fill kernel of every forward
+    size_t marks_off, marks_bytes;  // u8  [3][B][bpc]: block holds a positive / negative / mixed cell
+    size_t head_off;                // int32 list counter (256 B)
     size_t loss_off, loss_bytes;    // double[kLossSlots][8] loss accumulators
+    size_t list_off, list_bytes;    // int2 (voxel, image) per (voxel, view) pair that received a pixel
     size_t hits_off, hits_bytes;    // optional int32 per-pixel hit voxel
     size_t total;
 };
 
 Layout make_layout(const spsg_raycast_params *p) {
     Layout L;
-    L.n4x = (p->dimx + kFine - 1) >> kFineLog2;
-    L.n4y = (p->dimy + kFine - 1) >> kFineLog2;
-    L.n4z = (p->dimz + kFine - 1) >> kFineLog2;
+    L.nbx = (p->dimx + kFine - 1) >> kFineLog2;
+    L.nby = (p->dimy + kFine - 1) >> kFineLog2;
+    L.nbz = (p->dimz + kFine - 1) >> kFineLog2;
+    L.bpc = align_up((size_t)L.nbx * L.nby * L.nbz, 16);
     const int F = p->views_per_chunk > 0 ? p->views_per_chunk : 1;
+    const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
     size_t off = 0;
     L.dense_off = off;
-    L.dense_bytes = align_up((size_t)p->num_chunks * p->dimz * p->dimy * p->dimx * sizeof(float), 256);
+    L.dense_bytes = align_up(cells * sizeof(float), 256);
     off += L.dense_bytes;
-    L.skip_off = off;
-    L.skip_bytes = align_up((size_t)p->num_chunks * L.n4x * L.n4y * L.n4z, 256);
-    off += L.skip_bytes;
-    L.wpr = (p->dimx + 31) / 32;
-    L.vbit_off = off;
-    L.vbit_bytes = align_up((size_t)p->num_chunks * p->dimz * p->dimy * L.wpr * sizeof(uint2), 256);
-    off += L.vbit_bytes;
-    L.list_off = off;
-    L.list_bytes = align_up(256 + (size_t)(p->num_locs > 0 ? p->num_locs : 0) * 2 * sizeof(int32_t), 256);
-    off += L.list_bytes;
+    L.cmap_off = off;
+    L.cmap_bytes = align_up(cells, 256);
+    off += L.cmap_bytes;
+    L.bmap_off = off;
+    L.bmap_bytes = align_up((size_t)p->num_chunks * L.bpc, 256);
+    off += L.bmap_bytes;
+    L.zero_off = off;
+    L.marks_off = off;
+    L.marks_bytes = align_up((size_t)3 * p->num_chunks * L.bpc, 256);
+    off += L.marks_bytes;
+    L.head_off = off;
+    off += 256;
     L.loss_off = off;
     L.loss_bytes = align_up((size_t)kLossSlots * 8 * sizeof(double), 256);
     off += L.loss_bytes;
+    L.zero_bytes = off - L.zero_off;
+    L.list_off = off;
+    L.list_bytes = align_up((size_t)(p->num_locs > 0 ? p->num_locs : 0) * F * 2 * sizeof(int32_t), 256);
+    off += L.list_bytes;
     L.hits_off = off;
     L.hits_bytes = align_up((size_t)p->num_chunks * F * p->width * p->height * sizeof(int32_t), 256);
     off += L.hits_bytes;
@@ -301,8 +322,34 @@ __device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float 
 }
 
 // ---------------------------------------------------------------------------------------------
-// index + dense brick + skip hierarchy
+// per-call preparation: fill, index + dense brick, cell classes, block map
 // ---------------------------------------------------------------------------------------------
+
+// One launch instead of the reference's memsets (kernel.cu:475,483,515): up to three word-filled regions.
+struct FillArgs {
+    uint32_t *ptr[3];
+    size_t words[3];
+    uint32_t value[3];
+};
+
+__global__ void __launch_bounds__(256) fill_kernel(const FillArgs a) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        uint32_t *p = a.ptr[r];
+        const size_t n = a.words[r];
+        if (!p || n == 0) continue;
+        const uint32_t v = a.value[r];
+        if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+            const size_t n4 = n >> 2;
+            uint4 *p4 = reinterpret_cast<uint4 *>(p);
+            for (size_t i = tid; i < n4; i += stride) p4[i] = make_uint4(v, v, v, v);
+            for (size_t i = (n4 << 2) + tid; i < n; i += stride) p[i] = v;
+        } else {
+            for (size_t i = tid; i < n; i += stride) p[i] = v;
+        }
+    }
+}
 
 // construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + dense SDF scatter + voxel->pixel counter reset,
 // one pass over locs.
@@ -330,13 +377,14 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
 //            >= 0, they sum to ~1 so one is >= 1/8, and products with values above kTiny cannot underflow;
 //   negative likewise with all corners in (-kHuge, -kTiny): value < 0;
 //   mixed    all present, anything else: the value has to be computed.
-// Encoded in two bit planes per 32 cells of an x row (see Layout).  One warp per 32 cells; also marks every 4^3
-// block that holds at least one valid cell.
+// One byte per cell; one warp per 32 cells of an x row.  Also marks, per 4^3 block, whether it holds a positive, a
+// negative or a mixed cell (three byte planes, plain stores of 1: a benign race).
 constexpr float kTiny = 1e-30f, kHuge = 3e38f;
 
-__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
-                                                         uint8_t *__restrict__ skip, int num_chunks, int dimz, int dimy,
-                                                         int dimx, int wpr, int n4z, int n4y, int n4x) {
+__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint8_t *__restrict__ cmap,
+                                                         uint8_t *__restrict__ marks, size_t plane_stride,
+                                                         int num_chunks, int dimz, int dimy, int dimx, int wpr, int nbz,
+                                                         int nby, int nbx, size_t bpc) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long rows = (long long)num_chunks * dimz * dimy;
@@ -346,14 +394,15 @@ __global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict
     const int y = (int)(row % dimy); row /= dimy;
     const int z = (int)(row % dimz);
     const int chunk = (int)(row / dimz);
-    const float *__restrict__ base = dense + (size_t)chunk * dimz * dimy * dimx;
+    const size_t cells = (size_t)dimz * dimy * dimx;
+    const float *__restrict__ base = dense + (size_t)chunk * cells;
     const bool inner = (y + 1 < dimy) && (z + 1 < dimz);  // warp-uniform
+    const size_t o00 = ((size_t)z * dimy + y) * dimx;
     // per x column (x, y..y+1, z..z+1): all present / all positive class / all negative class
     bool col = false, pos = false, neg = false, coln = false, posn = false, negn = false;
+    const int x = xw * 32 + lane;
     if (inner) {
-        const size_t o00 = ((size_t)z * dimy + y) * dimx, o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx,
-                     o11 = o01 + dimx;
-        const int x = xw * 32 + lane;
+        const size_t o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx, o11 = o01 + dimx;
         if (x < dimx) {
             const float a = __ldg(base + o00 + x), b = __ldg(base + o10 + x), c = __ldg(base + o01 + x),
                         d = __ldg(base + o11 + x);
@@ -378,24 +427,39 @@ __global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict
     const unsigned nb = __ballot_sync(0xffffffffu, neg), nbn = __ballot_sync(0xffffffffu, negn);
     const unsigned v = SPSG_PAIR(cb, cbn), vp = SPSG_PAIR(pb, pbn), vn = SPSG_PAIR(nb, nbn);
 #undef SPSG_PAIR
-    if (lane == 0) vbits[warp] = make_uint2(v & ~vn, v & ~vp);
-    if (lane < 8 && ((v >> (4 * lane)) & 0xfu)) {
-        const int bx = xw * 8 + lane;
-        uint8_t *m = skip + (((size_t)chunk * n4z + (z >> kFineLog2)) * n4y + (y >> kFineLog2)) * n4x + bx;
-        if (*reinterpret_cast<volatile uint8_t *>(m) == 0) *m = 1;  // benign race: everybody writes 1
+    const unsigned vm = v & ~vp & ~vn;
+    if (x < dimx) {
+        const unsigned bit = 1u << lane;
+        const uint8_t cls = !(v & bit) ? kCellInvalid : (vp & bit) ? kCellPos : (vn & bit) ? kCellNeg : kCellMixed;
+        cmap[(size_t)chunk * cells + o00 + x] = cls;
+    }
+    if (lane < 24) {  // lanes 0-7: positive plane, 8-15: negative, 16-23: mixed; 4 cells of one block per lane
+        const int plane = lane >> 3, g = lane & 7;
+        const unsigned m = plane == 0 ? vp : plane == 1 ? vn : vm;
+        if ((m >> (4 * g)) & 0xfu) {
+            const int bx = xw * 8 + g;
+            uint8_t *t = marks + (size_t)plane * plane_stride + (size_t)chunk * bpc +
+                         ((size_t)(z >> kFineLog2) * nby + (y >> kFineLog2)) * nbx + bx;
+            if (*reinterpret_cast<volatile uint8_t *>(t) == 0) *t = 1;  // benign race: everybody writes 1
+        }
     }
 }
 
-// Turns the block marks (1 = some sample cell of this 4^3 block is valid) into skip levels, in place:
-//   0 = marked; k >= 1 = the aligned block of edge 2^(k+1) voxels (4, 8, 16, 32) around it has no valid sample cell.
-// One CTA per 32^3-voxel super block (8^3 fine blocks).
-__global__ void __launch_bounds__(512) skip_hierarchy_kernel(uint8_t *__restrict__ skip, int n4z, int n4y, int n4x,
-                                                             int sbz, int sby, int sbx) {
-    __shared__ int occ8[64], occ16[8], occ32;
+// Block map.  bits of a region = OR over its cells of {1: positive cell, 2: negative cell, 4: mixed cell}.  A region
+// is sign-uniform when it has no mixed cell and not both signs; empty when it has no valid cell at all.  Every 4^3
+// block gets the largest aligned region (edge 4, 8, 16, 32 = level 1..4) around it that is uniform:
+//   empty     if that region is empty, or no larger than the largest empty region around the block (one jump);
+//   positive / negative otherwise (two events: jump to the region's last sample, then step out);
+//   surface   (byte 0) if even the block itself is not uniform: samples there are classified cell by cell.
+// One CTA per 32^3-voxel super block (8^3 blocks).
+__global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restrict__ marks, size_t plane_stride,
+                                                        uint8_t *__restrict__ bmap, size_t bpc, int nbz, int nby,
+                                                        int nbx, int sbz, int sby, int sbx) {
+    __shared__ int agg8[64], agg16[8], agg32;
     const int t = threadIdx.x;
-    if (t < 64) occ8[t] = 0;
-    if (t < 8) occ16[t] = 0;
-    if (t == 0) occ32 = 0;
+    if (t < 64) agg8[t] = 0;
+    if (t < 8) agg16[t] = 0;
+    if (t == 0) agg32 = 0;
     __syncthreads();
     int sb = blockIdx.x;
     const int bx = sb % sbx; sb /= sbx;
@@ -404,25 +468,32 @@ __global__ void __launch_bounds__(512) skip_hierarchy_kernel(uint8_t *__restrict
     const int chunk = sb / sbz;
     const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
     const int fx = bx * kSuper + tx, fy = by * kSuper + ty, fz = bz * kSuper + tz;
-    const bool inside = fx < n4x && fy < n4y && fz < n4z;
-    uint8_t *m = skip + (((size_t)chunk * n4z + fz) * n4y + fy) * n4x + fx;
-    const bool occ = inside && (*m != 0);
-    if (occ) {
-        occ8[(tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1)] = 1;
-        occ16[(tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2)] = 1;
-        occ32 = 1;
+    const bool inside = fx < nbx && fy < nby && fz < nbz;
+    const size_t at = (size_t)chunk * bpc + ((size_t)fz * nby + fy) * nbx + fx;
+    int bits = 0;
+    if (inside)
+        bits = (marks[at] ? 1 : 0) | (marks[plane_stride + at] ? 2 : 0) | (marks[2 * plane_stride + at] ? 4 : 0);
+    const int i8 = (tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1), i16 = (tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2);
+    if (bits) {
+        atomicOr(&agg8[i8], bits);
+        atomicOr(&agg16[i16], bits);
+        atomicOr(&agg32, bits);
     }
     __syncthreads();
     if (inside) {
-        uint8_t level = 0;
-        if (!occ) {
-            level = 1;
-            if (!occ8[(tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1)]) {
-                level = 2;
-                if (!occ16[(tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2)]) level = occ32 ? 3 : 4;
-            }
+        const int r[5] = {0, bits, agg8[i8], agg16[i16], agg32};
+        int lu = 0, le = 0;  // largest uniform / largest empty level (regions nest, so the predicates are monotone)
+#pragma unroll
+        for (int l = 1; l <= 4; l++) {
+            if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
+            if (r[l] == 0) le = l;
         }
-        *m = level;
+        uint8_t byte = 0;
+        if (lu > 0) {
+            const int kind = (le == lu) ? kKindEmpty : (r[lu] & 1) ? kKindPos : kKindNeg;
+            byte = (uint8_t)((kind << 3) | lu);
+        }
+        bmap[at] = byte;
     }
 }
 
@@ -445,14 +516,16 @@ struct ForwardArgs {
     float *image_color, *image_depth, *image_normal, *image_semantic;
     int32_t *mapping3dto2d, *mapping3dto2d_num;
     const float *dense;
-    const uint8_t *skip;
-    const uint2 *vbits;
-    int wpr;
+    const uint8_t *cmap, *bmap;
+    size_t bpc;
+    int bmap_in_smem;
+    int32_t *list_count;
+    int2 *list;
     int32_t *hits;
     int width, height;
     float depth_min, depth_max, thresh, inc;
     int dimx, dimy, dimz;
-    int n4x, n4y, n4z;
+    int nbx, nby, nbz;
     int views, max_pixels;
     long long num_locs;
     unsigned flags;
@@ -499,11 +572,12 @@ __device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, flo
 // loss.py:246-257, train.py:744-746) to the epilogue.
 template <bool kLoss>
 __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const ForwardArgs a) {
-    // per-warp staging of the rendered tile: the kernel has no block-wide barrier, warps retire independently
+    // per-warp staging of the rendered tile (warps retire independently)
     __shared__ __align__(16) float s_sem_all[kTilePix * 14];
     __shared__ __align__(16) float s_col_all[kTilePix * 3];
     __shared__ __align__(16) float s_nrm_all[kTilePix * 3];
     __shared__ __align__(16) float s_dep_all[kTilePix];
+    extern __shared__ __align__(16) uint8_t s_bmap[];  // this chunk's block map (when it fits)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
@@ -515,36 +589,49 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
     const unsigned pix = uy * a.width + ux;
     const size_t gpix = (size_t)img * a.width * a.height + pix;
 
+    const uint8_t *__restrict__ gbmap = a.bmap + (size_t)chunk * a.bpc;
+    if (a.bmap_in_smem) {  // issue the copy first: its latency hides behind the ray setup
+        const uint4 *src = reinterpret_cast<const uint4 *>(gbmap);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bmap);
+        for (int i = threadIdx.x; i < (int)(a.bpc >> 4); i += kTilePix) dst[i] = __ldg(src + i);
+    }
+
     int hit = -1;
     float depth = 0.0f;
 
-    {
-        // Lanes outside the image run the same warp-synchronous loops below with an exhausted ray.
-        const int img_c = img;
-        const Ray r = setup_ray(a.view_matrix + (size_t)img_c * 16, a.intrinsics + (size_t)img_c * 4,
-                                active ? ux : 0u, active ? uy : 0u, a.depth_min, a.depth_max);
-        const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
-        Volume v;
-        v.index = a.sparse_mapping + (size_t)chunk * cells;
-        v.sdf = a.vals_sdf;
-        v.dense = a.dense + (size_t)chunk * cells;
-        v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
-        const uint8_t *__restrict__ skipmap = a.skip + (size_t)chunk * a.n4z * a.n4y * a.n4x;
-        const uint2 *__restrict__ vbits = a.vbits + (size_t)chunk * a.dimz * a.dimy * a.wpr;
-        const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
-        const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
-        const bool fast_ok = max(a.dimx, max(a.dimy, a.dimz)) <= kMaxFastDim;
-        const float kInf = CUDART_INF_F;
-        // approximate reciprocals are only used to size jumps; every margin below dwarfs their error
-        const float invx = r.dx != 0.0f ? rcp_approx(r.dx) : 0.0f, invy = r.dy != 0.0f ? rcp_approx(r.dy) : 0.0f,
-                    invz = r.dz != 0.0f ? rcp_approx(r.dz) : 0.0f;
-        Stepper step;
-        step.init(a.inc);
+    // Lanes outside the image run the same loops below with an exhausted ray.
+    const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, active ? ux : 0u,
+                            active ? uy : 0u, a.depth_min, a.depth_max);
+    const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
+    Volume v;
+    v.index = a.sparse_mapping + (size_t)chunk * cells;
+    v.sdf = a.vals_sdf;
+    v.dense = a.dense + (size_t)chunk * cells;
+    v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
+    const uint8_t *__restrict__ cmap = a.cmap + (size_t)chunk * cells;
+    const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
+    const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
+    const bool fast_ok = max(a.dimx, max(a.dimy, a.dimz)) <= kMaxFastDim;
+    const float kInf = CUDART_INF_F;
+    // approximate reciprocals are only used to size jumps; every margin below dwarfs their error
+    const float invx = r.dx != 0.0f ? rcp_approx(r.dx) : 0.0f, invy = r.dy != 0.0f ? rcp_approx(r.dy) : 0.0f,
+                invz = r.dz != 0.0f ? rcp_approx(r.dz) : 0.0f;
+    Stepper step;
+    step.init(a.inc);
 
-        float ray = r.t0, t_end = active ? r.t1 : -kInf;
-        if (clip && active) {
-            // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
-            float tin = -kInf, tout = kInf;
+    float ray = r.t0, t_end = active ? r.t1 : -kInf;
+    // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (Stepper): cap j so that this
+    // drift stays below kBoxEps / 4, far inside the kBoxEps the skip regions are shrunk by.
+    int jump_cap = 1 << 22;
+    {
+        const float top = fmaxf(fabsf(r.t1), 1.0f);
+        const float ulp = __uint_as_float(__float_as_uint(top) & 0x7f800000u) * 1.1920928955078125e-07f;
+        const float cap = (0.5f * kBoxEps) / ulp;
+        jump_cap = cap < 4194304.0f ? max(1, __float2int_rd(cap)) : (1 << 22);
+    }
+    if (clip && active) {
+        // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
+        float tin = -kInf, tout = kInf;
 #define SPSG_SLAB(o, d, inv, lo, hi)                                        \
     if ((d) != 0.0f) {                                                      \
         const float ta_ = ((lo) - (o)) * (inv), tb_ = ((hi) - (o)) * (inv); \
@@ -554,166 +641,174 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
         tin = kInf;                                                         \
         tout = -kInf;                                                       \
     }
-            SPSG_SLAB(r.camx, r.dx, invx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps)
-            SPSG_SLAB(r.camy, r.dy, invy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps)
-            SPSG_SLAB(r.camz, r.dz, invz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps)
+        SPSG_SLAB(r.camx, r.dx, invx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps)
+        SPSG_SLAB(r.camy, r.dy, invy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps)
+        SPSG_SLAB(r.camz, r.dz, invz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps)
 #undef SPSG_SLAB
-            const float margin = 0.0625f;
-            if (!(tin <= tout)) {
-                t_end = -kInf;  // misses the grid: nothing to march
-            } else {
-                t_end = fminf(t_end, tout + margin);
-                // jump to (at most) the last sample before tin - margin
-                while (ray < tin - margin - a.inc && ray < t_end) {
-                    const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, 1 << 22));
-                    ray = step.advance(ray, want);
+        const float margin = 0.0625f;
+        if (!(tin <= tout)) {
+            t_end = -kInf;  // misses the grid: nothing to march
+        } else {
+            t_end = fminf(t_end, tout + margin);
+            // jump to (at most) the last sample before tin - margin
+            while (ray < tin - margin - a.inc && ray < t_end) {
+                const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, jump_cap));
+                ray = step.advance(ray, want);
+            }
+        }
+    }
+
+    if (a.bmap_in_smem) __syncthreads();  // the block map copy has landed
+    const uint8_t *bmap = a.bmap_in_smem ? s_bmap : gbmap;
+
+    // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the sign the
+    // cell class guarantees; the value is computed if and when a crossing needs it.
+    float last_sdf = 0.0f, last_alpha = 0.0f;
+    bool last_ok = false, last_lazy = false;
+    float dist = 0.0f;
+    enum { kMarch = 0, kCross = 1, kDone = 2 };
+    int state = kMarch;
+    const unsigned kFull = 0xffffffffu;
+
+    for (;;) {
+        // ---- march.  The loop is warp-synchronous: all lanes take part in every vote and every iteration handles one
+        // event per marching lane, so diverged lanes re-join at the bottom of each iteration instead of running their
+        // iterations one group after the other.  An event is either a jump over samples whose outcome is known from
+        // the block map, or one sample.
+        while (__any_sync(kFull, state == kMarch)) {
+            if (state == kMarch) {
+                if (!(ray < t_end)) {  // kernel.cu:200
+                    state = kDone;
+                } else {
+                    enum { kActExact = 0, kActDense = 1, kActInvalid = 2, kActSign = 3, kActJumpEmpty = 4, kActJumpSame = 5 };
+                    int act = kActExact, nadv = 1;
+                    float sgn = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f;
+                    int ix = 0, iy = 0, iz = 0;
+                    const float px = __fmaf_rn(r.dx, ray, r.camx), py = __fmaf_rn(r.dy, ray, r.camy),
+                                pz = __fmaf_rn(r.dz, ray, r.camz);
+                    if (skip && fast_ok) {
+                        const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+                        ix = __float2int_rz(fx); iy = __float2int_rz(fy); iz = __float2int_rz(fz);
+                        if ((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
+                            (unsigned)iz < (unsigned)a.dimz) {
+                            const int b = bmap[((iz >> kFineLog2) * a.nby + (iy >> kFineLog2)) * a.nbx + (ix >> kFineLog2)];
+                            // the cell class is fetched alongside (independent address): one memory round trip per event
+                            const int cls = cmap[((size_t)iz * a.dimy + iy) * a.dimx + ix];
+                            wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
+                            if (b != 0) {
+                                // p is inside an aligned uniform region of edge `size`.  If it is at least kBoxEps inside
+                                // on every axis, corner (0,0,0) of this sample and of every later one up to the region's
+                                // exit lies in the region.
+                                const int kind = b >> 3, size = 2 << (b & 7), mask = ~(size - 1);
+                                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
+                                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
+                                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
+                                // a sign-uniform region cannot be jumped while the last valid sample has the other sign:
+                                // its first valid sample would be a crossing
+                                const bool opposite = last_ok && ((kind == kKindPos && last_sdf < 0.0f) ||
+                                                                  (kind == kKindNeg && last_sdf > 0.0f));
+                                if (!opposite && px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz) {
+                                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
+                                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
+                                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
+                                    const float tout = fminf(tx_, fminf(ty_, tz_));
+                                    // steps to the first sample beyond the region's exit
+                                    int n = 1;
+                                    if (tout > ray) n = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, jump_cap));
+                                    if (kind == kKindEmpty) {
+                                        // every sample before that one is invalid (kernel.cu:131,259)
+                                        act = kActJumpEmpty; nadv = n;
+                                    } else if (n >= 2) {
+                                        // Samples up to the last one inside are invalid or share the region's sign, and
+                                        // so does the last valid one before them: no crossing.  Land on the last one
+                                        // inside; it is classified by its own cell and leaves the march state exactly as
+                                        // the reference's sample-by-sample walk would.
+                                        act = kActJumpSame; nadv = n - 1;
+                                    }
+                                }
+                            }
+                            if (act == kActExact && frac_guard_ok(wx, wy, wz)) {
+                                // One sample, decided by its own cell.  With frac(p) clear of the cell faces the
+                                // reference's corners are exactly floor(p) + {0,1}; the cell's class says whether all 8
+                                // are present and whether they share a sign.
+                                if (cls == kCellInvalid) {
+                                    act = kActInvalid;
+                                } else {
+                                    act = kActDense;
+                                    if (cls != kCellMixed) {
+                                        sgn = cls == kCellPos ? 1.0f : -1.0f;
+                                        // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN)
+                                        if (!(last_ok && __fmul_rn(last_sdf, sgn) < 0.0f)) act = kActSign;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (act <= kActDense) {
+                        bool valid;
+                        if (act == kActDense) {
+                            dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
+                            valid = dist == dist;
+                        } else {
+                            valid = sample_sdf(v, fast_ok, px, py, pz, dist);  // the reference's exact corner arithmetic
+                        }
+                        if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
+                            state = kCross;
+                        } else if (valid) {
+                            last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                        } else {
+                            last_ok = false;  // :259
+                        }
+                    } else if (act == kActSign) {
+                        last_sdf = sgn; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
+                    } else if (act != kActJumpSame) {
+                        last_ok = false;  // :259 (invalid sample, or a run of them)
+                    }
+                    if (state == kMarch) ray = (nadv == 1) ? __fadd_rn(ray, a.inc) : step.advance(ray, nadv);  // :257,:260
                 }
             }
         }
-
-        // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the sign the
-        // cell class guarantees; the value is computed if and when a crossing needs it.
-        float last_sdf = 0.0f, last_alpha = 0.0f;
-        bool last_ok = false, last_lazy = false;
-
-        // Per-sample state machine.  Every sample of the reference's march is in exactly one state:
-        //   kJump   inside an aligned block without valid cells: invalid, and so is everything up to the block's exit
-        //   kStep   invalid cell, or valid cell whose sign is known and does not cross: nothing to compute
-        //   kEval   the trilinear value is needed (mixed-sign cell or possible crossing); kEvalExact: edge case that
-        //           has to go through the reference's exact corner arithmetic
-        //   kCross  sign change found, waiting for the warp's refinement round;  kDone: ray exhausted or pixel hit
-        // The loop below is warp-synchronous (every lane of the warp takes part in every __any_sync): per iteration each
-        // lane handles one event, all lanes classify their next sample together, and refinements are batched.
-        enum { kJump = 0, kStep = 1, kEval = 2, kEvalExact = 3, kCross = 4, kDone = 5 };
-        const unsigned kFull = 0xffffffffu;
-        float px = 0.0f, py = 0.0f, pz = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f, dist = 0.0f;
-        int ix = 0, iy = 0, iz = 0, level = 0;
-        float step_sign = 0.0f;  // kStep: 0 = invalid cell, +-1 = valid cell with that sign
-        auto classify = [&]() -> int {
-            if (!(ray < t_end)) return kDone;  // kernel.cu:200
-            px = __fmaf_rn(r.dx, ray, r.camx);
-            py = __fmaf_rn(r.dy, ray, r.camy);
-            pz = __fmaf_rn(r.dz, ray, r.camz);
-            if (!skip) return kEvalExact;
-            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-            ix = __float2int_rz(fx); iy = __float2int_rz(fy); iz = __float2int_rz(fz);
-            if (!((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy && (unsigned)iz < (unsigned)a.dimz))
-                return kEvalExact;
-            // both lookups are issued together (independent addresses): one memory round trip per sample
-            level = skipmap[((iz >> kFineLog2) * a.n4y + (iy >> kFineLog2)) * a.n4x + (ix >> kFineLog2)];
-            const uint2 word = __ldg(vbits + ((size_t)iz * a.dimy + iy) * a.wpr + (ix >> 5));
-            if (level != 0) return kJump;
-            if (!fast_ok) return kEvalExact;
-            // Block with valid cells: decide this sample by its own cell.  With frac(p) clear of the cell faces the
-            // reference's corners are exactly floor(p) + {0,1}, and the cell's class bits say whether all 8 are present
-            // and whether they share a sign.
-            wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
-            if (!frac_guard_ok(wx, wy, wz)) return kEvalExact;
-            const unsigned ca = (word.x >> (ix & 31)) & 1u, cb = (word.y >> (ix & 31)) & 1u;
-            if ((ca | cb) == 0u) { step_sign = 0.0f; return kStep; }
-            if ((ca & cb) != 0u) return kEval;
-            step_sign = ca ? 1.0f : -1.0f;
-            // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN: it came from a valid, non-NaN sample)
-            return (last_ok && __fmul_rn(last_sdf, step_sign) < 0.0f) ? kEval : kStep;
-        };
-
-        int state = classify();
-        for (;;) {
-            if (!__any_sync(kFull, state <= kEvalExact)) {
-                // ---- refinement round: every lane is either waiting with a crossing or finished
-                if (!__any_sync(kFull, state == kCross)) break;
-                if (state == kCross) {
-                    if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
-                        float dl = last_sdf;
-                        if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
-                                       __fmaf_rn(r.dz, last_alpha, r.camz), dl))
-                            last_sdf = dl;
-                        last_lazy = false;
-                    }
-                    // findIntersectionBisection (:166-187)
-                    float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
-                    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-                    bool ok = true;
-#pragma unroll 1
-                    for (int k = 0; k < 3; k++) {
-                        c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
-                        cx = __fmaf_rn(r.dx, c, r.camx);
-                        cy = __fmaf_rn(r.dy, c, r.camy);
-                        cz = __fmaf_rn(r.dz, c, r.camz);
-                        float dc;
-                        if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
-                            ok = false;
-                            break;
-                        }
-                        if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
-                    }
-                    if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
-                        depth = __fdiv_rn(c, r.d2r);                                                     // :215
-                        // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel
-                        // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
-                        // ever says otherwise the reference reads stale registers -- we keep marching instead.
-                        const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
-                        hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
-                    }
-                    if (hit >= 0) {
-                        state = kDone;
-                    } else {
-                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
-                        ray = __fadd_rn(ray, a.inc);                                           // :257
-                        state = classify();
-                    }
-                }
-                continue;
+        // ---- refinement round: every lane is either waiting with a crossing or finished
+        if (!__any_sync(kFull, state == kCross)) break;
+        if (state == kCross) {
+            if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
+                float dl = last_sdf;
+                if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
+                               __fmaf_rn(r.dz, last_alpha, r.camz), dl))
+                    last_sdf = dl;
+                last_lazy = false;
             }
-            // ---- one event per lane and iteration; the three handlers are warp-uniform blocks of code
-            if (state == kStep) {
-                if (step_sign == 0.0f) {
-                    last_ok = false;  // kernel.cu:259
-                } else {
-                    last_sdf = step_sign; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
+            // findIntersectionBisection (:166-187)
+            float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
+            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+            bool ok = true;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
+                cx = __fmaf_rn(r.dx, c, r.camx);
+                cy = __fmaf_rn(r.dy, c, r.camy);
+                cz = __fmaf_rn(r.dz, c, r.camz);
+                float dc;
+                if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
+                    ok = false;
+                    break;
                 }
-                ray = __fadd_rn(ray, a.inc);  // :257,:260
-                state = classify();
-            } else if (state == kJump) {
-                // p is inside an aligned block of edge `size` without any valid sample cell.  If it is at least
-                // kBoxEps inside on every axis, the sample's corner (0,0,0) lies in the block: the sample is invalid
-                // (kernel.cu:131,259) and so is every later one up to the block's exit.
-                const int size = 2 << level, mask = ~(size - 1);
-                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
-                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
-                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
-                if (!(px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz)) {
-                    state = kEvalExact;  // within kBoxEps of the block's faces: let the exact path decide
-                } else {
-                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
-                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
-                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
-                    const float tout = fminf(tx_, fminf(ty_, tz_));
-                    int want = 1;
-                    if (tout > ray) want = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, 1 << 22));
-                    last_ok = false;  // kernel.cu:259
-                    ray = step.advance(ray, want);
-                    state = classify();
-                }
-            } else if (state == kEval || state == kEvalExact) {
-                bool valid;
-                if (state == kEval) {
-                    dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
-                    valid = dist == dist;
-                } else {
-                    valid = sample_sdf(v, fast_ok, px, py, pz, dist);
-                }
-                if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
-                    state = kCross;
-                } else {
-                    if (valid) {
-                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
-                    } else {
-                        last_ok = false;  // :259
-                    }
-                    ray = __fadd_rn(ray, a.inc);  // :257,:260
-                    state = classify();
-                }
+                if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+            }
+            if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
+                depth = __fdiv_rn(c, r.d2r);                                                     // :215
+                // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel
+                // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
+                // ever says otherwise the reference reads stale registers -- we keep marching instead.
+                const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
+                hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
+            }
+            if (hit >= 0) {
+                state = kDone;
+            } else {
+                last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                ray = __fadd_rn(ray, a.inc);                                           // :257
+                state = kMarch;
             }
         }
     }
@@ -728,6 +823,7 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
 #pragma unroll
     for (int k = 0; k < 14; k++) sem[k] = ninf;
     float n0 = ninf, n1 = ninf, n2 = ninf;
+    bool first = false;
     if (hit >= 0) {
         const float *c = a.vals_color + (size_t)hit * 3, *n = a.vals_normal + (size_t)hit * 3;
         col0 = __ldg(c + 0); col1 = __ldg(c + 1); col2 = __ldg(c + 2);
@@ -743,6 +839,17 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
         const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
         const int offset = atomicAdd(a.mapping3dto2d_num + row, 1);                            // :244
         if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;  // :245-247
+        first = offset == 0;
+    }
+    {
+        // the first pixel of a (voxel, view) pair appends the pair to the backward's work list (one atomic per warp)
+        const unsigned m = __ballot_sync(kFull, first);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
+            base = __shfl_sync(kFull, base, 0);
+            if (first) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(hit, img);
+        }
     }
     s_col[tp * 3 + 0] = col0; s_col[tp * 3 + 1] = col1; s_col[tp * 3 + 2] = col2;
     s_nrm[tp * 3 + 0] = n0; s_nrm[tp * 3 + 1] = n1; s_nrm[tp * 3 + 2] = n2;
@@ -805,6 +912,7 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
 }
 
 
+
 // loss_out[0..3] = depth, colour, semantic, weighted total; [4..6] = normalisers the backward needs.
 __global__ void finalize_loss_kernel(const double *__restrict__ acc, float *__restrict__ out, float w_depth,
                                      float w_color, float w_sem, int has_depth, int has_color, int has_sem) {
@@ -831,170 +939,164 @@ struct BackwardArgs {
     const float *loss_out;
     float w_depth, w_color, w_sem;
     const float *grad_scale;  // device scalar or NULL (= 1)
-    const int32_t *sparse_mapping, *mapping3dto2d, *mapping3dto2d_num;
+    const int32_t *mapping3dto2d, *mapping3dto2d_num;
     float *d_color, *d_depth, *d_normal, *d_semantic;
-    int32_t *list_count;
-    int2 *list;
+    const int32_t *list_count;
+    const int2 *list;
     int width, height;
-    long long cells_per_chunk;
-    int num_chunks, views, max_pixels;
+    int views, max_pixels;
     long long num_locs;
+    int zero_blocks;  // leading CTAs of the launch that clear gradient rows instead of gathering
+    int vec4_ok;      // mapping3dto2d rows are 16-byte aligned
 };
 
-// Pass 1 (replaces the 4 memsets and the one-block-per-dense-voxel launch of kernel.cu:557-568): one thread per
-// dense cell; present voxels nobody hit get their 21 gradient slots zeroed, hit voxels are appended to a list.
-__global__ void __launch_bounds__(256) backward_scan_kernel(const BackwardArgs a) {
-    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = a.cells_per_chunk * a.num_chunks;
-    int idx = -1;
-    if (cell < total) idx = __ldg(a.sparse_mapping + cell);
-    bool hit = false;
-    if (idx >= 0) {
-        for (int f = 0; f < a.views; f++) hit |= __ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + idx) > 0;
-        if (!hit) {
-            float *c = a.d_color + (size_t)idx * 3, *n = a.d_normal + (size_t)idx * 3;
-            c[0] = 0.0f; c[1] = 0.0f; c[2] = 0.0f;
-            n[0] = 0.0f; n[1] = 0.0f; n[2] = 0.0f;
-            a.d_depth[idx] = 0.0f;
-            float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)idx * 14);
+// Clears the 21 gradient slots of voxels [0, N) (replaces the 4 whole-buffer memsets of kernel.cu:557-560).
+// kSkipHit (one view per chunk): rows of voxels that received pixels are left to the gather, which overwrites them.
+template <bool kSkipHit>
+__device__ __forceinline__ void zero_rows(const BackwardArgs &a, long long first, long long stride) {
+    for (long long i = first; i < a.num_locs; i += stride) {
+        if (kSkipHit && __ldg(a.mapping3dto2d_num + i) > 0) continue;
+        float *c = a.d_color + (size_t)i * 3, *n = a.d_normal + (size_t)i * 3;
+        c[0] = 0.0f; c[1] = 0.0f; c[2] = 0.0f;
+        n[0] = 0.0f; n[1] = 0.0f; n[2] = 0.0f;
+        a.d_depth[i] = 0.0f;
+        float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)i * 14);
 #pragma unroll
-            for (int k = 0; k < 7; k++) s[k] = make_float2(0.0f, 0.0f);
-        }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (hit) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(idx, (int)(cell / a.cells_per_chunk));
+        for (int k = 0; k < 7; k++) s[k] = make_float2(0.0f, 0.0f);
     }
 }
 
-// Upstream gradient of one pixel for this lane's channel.  Lanes 0-13 semantic, 16-18 colour, 19 depth,
-// 20-22 normal; other lanes idle.  Plain variant: one load from this lane's image (base pointer + per-pixel stride
-// prepared by lane_source).  Fused variant: recomputed from the rendering and the targets.
-struct LaneSource {
-    const float *base;  // nullptr: idle lane
-    unsigned stride;
-};
-
-__device__ __forceinline__ LaneSource lane_source(const BackwardArgs &a, int lane) {
-    LaneSource s;
-    s.base = nullptr; s.stride = 0;
-    if (lane < 14) { s.base = a.grad_semantic + lane; s.stride = 14; }
-    else if (lane >= 16 && lane < 19) { s.base = a.grad_color + (lane - 16); s.stride = 3; }
-    else if (lane == 19) { s.base = a.grad_depth; s.stride = 1; }
-    else if (lane >= 20 && lane < 23) { s.base = a.grad_normal + (lane - 20); s.stride = 3; }
-    return s;
+__global__ void __launch_bounds__(128) backward_zero_kernel(const BackwardArgs a) {
+    zero_rows<false>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
+// Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal),
+// accumulated as acc += g * inv (kernel.cu:398-418: val = grad / count, then add).  Plain variant: read from the four
+// gradient images.  Fused variant: recomputed from the rendering and the targets of the 2D losses.
 template <bool kFused>
-__device__ __forceinline__ float pixel_grad(const BackwardArgs &a, const LaneSource &src, int lane, unsigned gpix) {
+__device__ __forceinline__ void accumulate_pixel(const BackwardArgs &a, unsigned gpix, float inv, float (&acc)[21]) {
+    float g[21];
     if (!kFused) {
-        return src.base ? __ldg(src.base + (size_t)gpix * src.stride) : 0.0f;
+        const float2 *s2 = reinterpret_cast<const float2 *>(a.grad_semantic + (size_t)gpix * 14);
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const float2 t = __ldg(s2 + k);
+            g[2 * k] = t.x; g[2 * k + 1] = t.y;
+        }
+        const float *c = a.grad_color + (size_t)gpix * 3, *n = a.grad_normal + (size_t)gpix * 3;
+        g[14] = __ldg(c); g[15] = __ldg(c + 1); g[16] = __ldg(c + 2);
+        g[17] = __ldg(a.grad_depth + gpix);
+        g[18] = __ldg(n); g[19] = __ldg(n + 1); g[20] = __ldg(n + 2);
     } else {
         const LossArgs &L = a.loss;
-        float g = 0.0f;
+        const float scale = a.grad_scale ? __ldg(a.grad_scale) : 1.0f;
+#pragma unroll
+        for (int k = 0; k < 21; k++) g[k] = 0.0f;
         // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
         const int y = L.target_label ? (int)L.target_label[gpix] : 14;
-        float logit = (lane < 14) ? __ldg(a.image_semantic + (size_t)gpix * 14 + lane) : -CUDART_INF_F;
-        if (y < 14 && __shfl_sync(0xffffffffu, logit, 0) != -CUDART_INF_F) {  // warp-uniform: one pixel per iteration
-            float m = logit;
+        if (y < 14) {
+            float l[14];
+            const float2 *s2 = reinterpret_cast<const float2 *>(a.image_semantic + (size_t)gpix * 14);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float e = (lane < 14) ? expf(logit - m) : 0.0f;
-            float s = e;
+            for (int k = 0; k < 7; k++) {
+                const float2 t = __ldg(s2 + k);
+                l[2 * k] = t.x; l[2 * k + 1] = t.y;
+            }
+            if (l[0] != -CUDART_INF_F) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+                float m = l[0];
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane < 14) {
+                for (int k = 1; k < 14; k++) m = fmaxf(m, l[k]);
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 14; k++) {
+                    l[k] = expf(l[k] - m);
+                    sum += l[k];
+                }
                 const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
-                g = a.w_sem * w * (e / s - (lane == y ? 1.0f : 0.0f)) / a.loss_out[6];
+                const float f = a.w_sem * w, norm = a.loss_out[6];
+#pragma unroll
+                for (int k = 0; k < 14; k++) g[k] = f * (l[k] / sum - (k == y ? 1.0f : 0.0f)) / norm * scale;
             }
         }
-        if (lane >= 16 && lane < 19 && L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
+        if (L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
             const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
-            const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + (size_t)gpix * 3 + (lane - 16)), w),
-                                      -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + (lane - 16)), w));
-            g = a.w_color * ((d > 0.0f) - (d < 0.0f)) * w / a.loss_out[5];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + (size_t)gpix * 3 + k), w),
+                                          -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
+                g[14 + k] = a.w_color * ((d > 0.0f) - (d < 0.0f)) * w / a.loss_out[5] * scale;
+            }
         }
-        if (lane == 19 && L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
+        if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
             const float t = __ldg(L.target_depth + gpix);
             if (t != 0.0f) {
                 const float d = __fmul_rn(__ldg(a.image_depth + gpix), L.voxelsize) - t;
-                g = a.w_depth * ((d > 0.0f) - (d < 0.0f)) * L.voxelsize / a.loss_out[4];
+                g[17] = a.w_depth * ((d > 0.0f) - (d < 0.0f)) * L.voxelsize / a.loss_out[4] * scale;
             }
         }
-        return a.grad_scale ? g * __ldg(a.grad_scale) : g;
     }
+#pragma unroll
+    for (int k = 0; k < 21; k++) acc[k] = __fmaf_rn(g[k], inv, acc[k]);
 }
 
-// Pass 2: one warp per hit voxel, lane == channel.  The warp first fetches the voxel's per-view counters in one
-// round trip (lane == view), then the registered pixel ids of all views in a second one (flattened view-major
-// list, lane == list position), and finally streams the pixels' gradients eight at a time, accumulating grad/cnt
-// (kernel.cu:398-418) in list order -- a fixed order, hence deterministic.
-template <bool kFused>
-__global__ void __launch_bounds__(256) backward_gather_kernel(const BackwardArgs a) {
-    const unsigned kFull = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+// The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
+// thread per item: pair -> pixel count and first four registered pixel ids (one round trip) -> the pixels' 21 upstream
+// gradients (independent 8-byte / 4-byte loads), accumulated as grad / count in registration order -- a fixed order,
+// so with one view per chunk the result is deterministic and written with plain stores.  With several views per chunk
+// the per-view means of a voxel are summed with float atomics onto rows the zero kernel cleared (kAtomic).
+template <bool kFused, bool kAtomic>
+__global__ void __launch_bounds__(128) backward_gather_kernel(const BackwardArgs a) {
+    if ((int)blockIdx.x < a.zero_blocks) {
+        zero_rows<true>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)a.zero_blocks * blockDim.x);
+        return;
+    }
+    const int stride = (int)(gridDim.x - a.zero_blocks) * blockDim.x;
     const int count = *a.list_count;
     const unsigned P = (unsigned)(a.width * a.height);
-    const LaneSource src = lane_source(a, lane);
-    for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < count; item += warps_total) {
+    for (int item = ((int)blockIdx.x - a.zero_blocks) * blockDim.x + threadIdx.x; item < count; item += stride) {
         const int2 e = a.list[item];
-        const int vidx = e.x, chunk = e.y;
-        float acc = 0.0f;
-        for (int f0 = 0; f0 < a.views; f0 += 32) {  // views in groups of 32 (one per lane)
-            const int f = f0 + lane;
-            int cnt = 0;
-            if (f < a.views) cnt = min(max(__ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + vidx), 0), a.max_pixels);
-            // exclusive prefix sum of the counts over lanes
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int excl = incl - cnt;
-            const int total = __shfl_sync(kFull, incl, 31);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                // list position t0 + lane -> (view, slot): the view whose [excl, incl) range holds it
-                const int pos = t0 + lane;
-                int my_view = 0, my_excl = 0, my_cnt = 1;
-                for (int k = 0; k < min(32, a.views - f0); k++) {
-                    const int ek = __shfl_sync(kFull, excl, k), ck = __shfl_sync(kFull, cnt, k);
-                    if (pos >= ek && pos < ek + ck) { my_view = k; my_excl = ek; my_cnt = ck; }
-                }
-                unsigned my_pix = 0;  // global pixel index; < 2^32 / 14 (check_params)
-                if (pos < total) {
-                    const size_t row = (size_t)(f0 + my_view) * a.num_locs + vidx;
-                    my_pix = (unsigned)(chunk * a.views + f0 + my_view) * P +
-                             (unsigned)__ldg(a.mapping3dto2d + row * a.max_pixels + (pos - my_excl));
-                }
-                const float my_fcnt = __frcp_rn((float)my_cnt);
-                const int m = min(32, total - t0);
-                int t = 0;
-                for (; t + 8 <= m; t += 8) {  // 8 independent gathers in flight, summed in order
-                    float g[8], c[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        g[u] = pixel_grad<kFused>(a, src, lane, __shfl_sync(kFull, my_pix, t + u));
-                        c[u] = __shfl_sync(kFull, my_fcnt, t + u);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) acc = __fmaf_rn(g[u], c[u], acc);
-                }
-                for (; t < m; t++) {
-                    const float g = pixel_grad<kFused>(a, src, lane, __shfl_sync(kFull, my_pix, t));
-                    acc = __fmaf_rn(g, __shfl_sync(kFull, my_fcnt, t), acc);
-                }
-            }
+        const int idx = e.x, img = e.y;
+        const size_t row = (size_t)(img % a.views) * a.num_locs + idx;
+        const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
+        // both loads depend only on the pair: one round trip
+        int cnt = __ldg(a.mapping3dto2d_num + row);
+        int4 p4 = make_int4(0, 0, 0, 0);
+        if (a.vec4_ok) {
+            p4 = __ldg(reinterpret_cast<const int4 *>(prow));
+        } else {
+            p4.x = __ldg(prow);
+            if (a.max_pixels > 1) p4.y = __ldg(prow + 1);
+            if (a.max_pixels > 2) p4.z = __ldg(prow + 2);
+            if (a.max_pixels > 3) p4.w = __ldg(prow + 3);
         }
-        if (lane < 14) a.d_semantic[(size_t)vidx * 14 + lane] = acc;
-        else if (lane >= 16 && lane < 19) a.d_color[(size_t)vidx * 3 + (lane - 16)] = acc;
-        else if (lane == 19) a.d_depth[vidx] = acc;
-        else if (lane >= 20 && lane < 23) a.d_normal[(size_t)vidx * 3 + (lane - 20)] = acc;
+        cnt = min(max(cnt, 0), a.max_pixels);  // kernel.cu:392-393
+        const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
+        const float inv = __frcp_rn((float)max(cnt, 1));
+        float acc[21];
+#pragma unroll
+        for (int k = 0; k < 21; k++) acc[k] = 0.0f;
+        if (cnt > 0) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.x, inv, acc);
+        if (cnt > 1) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.y, inv, acc);
+        if (cnt > 2) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.z, inv, acc);
+        if (cnt > 3) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.w, inv, acc);
+#pragma unroll 1
+        for (int k = 4; k < cnt; k++) accumulate_pixel<kFused>(a, pixbase + (unsigned)__ldg(prow + k), inv, acc);
+        float *ds = a.d_semantic + (size_t)idx * 14, *dc = a.d_color + (size_t)idx * 3, *dn = a.d_normal + (size_t)idx * 3;
+        if (kAtomic) {
+#pragma unroll
+            for (int k = 0; k < 14; k++) atomicAdd(ds + k, acc[k]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) atomicAdd(dc + k, acc[14 + k]);
+            atomicAdd(a.d_depth + idx, acc[17]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) atomicAdd(dn + k, acc[18 + k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(ds)[k] = make_float2(acc[2 * k], acc[2 * k + 1]);
+            dc[0] = acc[14]; dc[1] = acc[15]; dc[2] = acc[16];
+            a.d_depth[idx] = acc[17];
+            dn[0] = acc[18]; dn[1] = acc[19]; dn[2] = acc[20];
+        }
     }
 }
 
@@ -1083,10 +1185,24 @@ int check_params(const spsg_raycast_params *p) {
         return fail(SPSG_ERR_INVALID_ARGUMENT, "dense grid exceeds 32-bit indexing (reference limit, SURVEY 3.5)");
     if ((long long)p->num_chunks * p->views_per_chunk * p->width * p->height * 14 >= (1ll << 32))
         return fail(SPSG_ERR_INVALID_ARGUMENT, "image batch exceeds 32-bit indexing (reference limit, SURVEY 3.5)");
+    if ((long long)p->num_locs * p->views_per_chunk >= (1ll << 31))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "num_locs * views_per_chunk exceeds 32-bit indexing");
     return SPSG_OK;
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = sms > 0 ? sms : 148;
+    }
+    return cached[dev];
+}
 
 LossArgs make_loss_args(const spsg_loss_targets *t, double *accum) {
     LossArgs L;
@@ -1116,21 +1232,30 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         return fail(SPSG_ERR_INVALID_ARGUMENT, "view_matrix / intrinsics must be 16-byte aligned");
     if (p->num_locs > 0 && ((reinterpret_cast<uintptr_t>(vals_semantic) & 7u) || (reinterpret_cast<uintptr_t>(locs) & 15u)))
         return fail(SPSG_ERR_INVALID_ARGUMENT, "vals_semantic must be 8-byte and locs 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(sparse_mapping) & 3u) return fail(SPSG_ERR_INVALID_ARGUMENT, "sparse_mapping must be 4-byte aligned");
     if (targets && !loss_out) return fail(SPSG_ERR_INVALID_ARGUMENT, "loss_out is NULL");
     const Layout L = make_layout(p);
     if (!workspace || workspace_bytes < L.total) return fail(SPSG_ERR_WORKSPACE_TOO_SMALL, "workspace too small");
     if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(SPSG_ERR_INVALID_ARGUMENT, "workspace must be 256-byte aligned");
     uint8_t *ws = (uint8_t *)workspace;
     float *dense = (float *)(ws + L.dense_off);
-    uint8_t *skip = ws + L.skip_off;
-    uint2 *vbits = (uint2 *)(ws + L.vbit_off);
+    uint8_t *cmap = ws + L.cmap_off, *bmap = ws + L.bmap_off, *marks = ws + L.marks_off;
     double *accum = (double *)(ws + L.loss_off);
     const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
+    const int sms = sm_count();
 
-    if (build_index) CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));  // kernel.cu:515
-    CUDA_TRY(cudaMemsetAsync(dense, 0xff, L.dense_bytes, st));  // 0xffffffff is a NaN: every voxel absent
-    CUDA_TRY(cudaMemsetAsync(skip, 0, L.skip_bytes, st));
-    if (targets) CUDA_TRY(cudaMemsetAsync(accum, 0, L.loss_bytes, st));
+    {
+        // sparse_mapping := -1 (kernel.cu:515), dense brick := NaN (0xffffffff: every voxel absent), block marks / list
+        // counter / loss accumulators := 0 -- one launch
+        FillArgs f;
+        f.ptr[0] = build_index ? (uint32_t *)sparse_mapping : nullptr; f.words[0] = cells; f.value[0] = 0xffffffffu;
+        f.ptr[1] = (uint32_t *)dense; f.words[1] = L.dense_bytes / 4; f.value[1] = 0xffffffffu;
+        f.ptr[2] = (uint32_t *)(ws + L.zero_off); f.words[2] = L.zero_bytes / 4; f.value[2] = 0u;
+        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4) / 4;
+        const unsigned blocks = (unsigned)std::min<size_t>((vecs + 1023) / 1024 + 1, (size_t)sms * 8);
+        fill_kernel<<<blocks, 256, 0, st>>>(f);
+        CUDA_TRY(cudaGetLastError());
+    }
     if (p->num_locs > 0) {
         const unsigned blocks = (unsigned)((p->num_locs + 255) / 256);
         if (build_index)
@@ -1143,15 +1268,18 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
                                                         p->dimx);
         CUDA_TRY(cudaGetLastError());
     }
+    const size_t plane_stride = (size_t)p->num_chunks * L.bpc;
     {
-        const long long vwarps = (long long)p->num_chunks * p->dimz * p->dimy * L.wpr;
-        cell_class_kernel<<<(unsigned)((vwarps + 7) / 8), 256, 0, st>>>(dense, vbits, skip, p->num_chunks, p->dimz,
-                                                                       p->dimy, p->dimx, L.wpr, L.n4z, L.n4y, L.n4x);
+        const int wpr = (p->dimx + 31) / 32;
+        const long long vwarps = (long long)p->num_chunks * p->dimz * p->dimy * wpr;
+        cell_class_kernel<<<(unsigned)((vwarps + 7) / 8), 256, 0, st>>>(dense, cmap, marks, plane_stride, p->num_chunks,
+                                                                       p->dimz, p->dimy, p->dimx, wpr, L.nbz, L.nby,
+                                                                       L.nbx, L.bpc);
         CUDA_TRY(cudaGetLastError());
-        const int sbx = (L.n4x + kSuper - 1) / kSuper, sby = (L.n4y + kSuper - 1) / kSuper,
-                  sbz = (L.n4z + kSuper - 1) / kSuper;
-        skip_hierarchy_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(skip, L.n4z, L.n4y, L.n4x,
-                                                                                           sbz, sby, sbx);
+        const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
+                  sbz = (L.nbz + kSuper - 1) / kSuper;
+        block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, plane_stride, bmap, L.bpc,
+                                                                                      L.nbz, L.nby, L.nbx, sbz, sby, sbx);
         CUDA_TRY(cudaGetLastError());
     }
     ForwardArgs a;
@@ -1162,12 +1290,15 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_color = image_color; a.image_depth = image_depth; a.image_normal = image_normal;
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
-    a.dense = dense; a.skip = skip; a.vbits = vbits; a.wpr = L.wpr;
+    a.dense = dense; a.cmap = cmap; a.bmap = bmap; a.bpc = L.bpc;
+    a.bmap_in_smem = L.bpc <= (size_t)kMaxSmemBlockMap;
+    a.list_count = (int32_t *)(ws + L.head_off);
+    a.list = (int2 *)(ws + L.list_off);
     a.hits = (p->flags & SPSG_FLAG_RECORD_HITS) ? (int32_t *)(ws + L.hits_off) : nullptr;
     a.width = p->width; a.height = p->height;
     a.depth_min = p->depth_min; a.depth_max = p->depth_max; a.thresh = p->thresh_sample_dist; a.inc = p->ray_increment;
     a.dimx = p->dimx; a.dimy = p->dimy; a.dimz = p->dimz;
-    a.n4x = L.n4x; a.n4y = L.n4y; a.n4z = L.n4z;
+    a.nbx = L.nbx; a.nby = L.nby; a.nbz = L.nbz;
     a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
     a.num_locs = p->num_locs;
     a.flags = p->flags;
@@ -1176,10 +1307,11 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.loss = make_loss_args(targets, accum);
     const dim3 grid((p->width + kTileW - 1) / kTileW, (p->height + kTileH - 1) / kTileH,
                     p->num_chunks * p->views_per_chunk);
+    const size_t dyn = a.bmap_in_smem ? L.bpc : 0;
     if (targets) {
         {
             ScopedKernelTimer timer(0, st);
-            raycast_forward_kernel<true><<<grid, kTilePix, 0, st>>>(a);
+            raycast_forward_kernel<true><<<grid, kTilePix, dyn, st>>>(a);
         }
         CUDA_TRY(cudaGetLastError());
         finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
@@ -1187,7 +1319,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
                                               targets->target_color != nullptr, targets->target_label != nullptr);
     } else {
         ScopedKernelTimer timer(0, st);
-        raycast_forward_kernel<false><<<grid, kTilePix, 0, st>>>(a);
+        raycast_forward_kernel<false><<<grid, kTilePix, dyn, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
@@ -1203,6 +1335,7 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
         !mapping3dto2d || !mapping3dto2d_num)
         return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL tensor pointer");
     if (fused && (!targets || !loss_out)) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL loss targets");
+    if (p->max_pixels_per_voxel <= 0) return fail(SPSG_ERR_INVALID_ARGUMENT, "max_pixels_per_voxel must be positive");
     if (p->num_locs == 0) return SPSG_OK;
     if (!d_color || !d_depth || !d_normal || !d_semantic) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer");
     if (reinterpret_cast<uintptr_t>(d_semantic) & 7u) return fail(SPSG_ERR_INVALID_ARGUMENT, "d_semantic must be 8-byte aligned");
@@ -1221,25 +1354,32 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
         a.grad_color = g_or_img_color; a.grad_depth = g_or_img_depth; a.grad_normal = grad_normal;
         a.grad_semantic = g_or_img_semantic;
     }
-    a.sparse_mapping = sparse_mapping; a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
+    a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
     a.d_color = d_color; a.d_depth = d_depth; a.d_normal = d_normal; a.d_semantic = d_semantic;
-    a.list_count = (int32_t *)(ws + L.list_off);
-    a.list = (int2 *)(ws + L.list_off + 256);
+    a.list_count = (const int32_t *)(ws + L.head_off);
+    a.list = (const int2 *)(ws + L.list_off);
     a.width = p->width; a.height = p->height;
-    a.cells_per_chunk = (long long)p->dimz * p->dimy * p->dimx;
-    a.num_chunks = p->num_chunks; a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
+    a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
     a.num_locs = p->num_locs;
-    CUDA_TRY(cudaMemsetAsync(a.list_count, 0, sizeof(int32_t), st));
-    const long long cells = a.cells_per_chunk * a.num_chunks;
-    backward_scan_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned blocks = (unsigned)(sms * 8);  // 8 resident 256-thread CTAs per SM, grid-stride over the list
-    {
+    a.vec4_ok = (p->max_pixels_per_voxel % 4 == 0) && aligned16(mapping3dto2d);
+    const int sms = sm_count();
+    // one thread per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
+    const long long max_items = p->num_locs * p->views_per_chunk;
+    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + 127) / 128, (long long)sms * 16));
+    const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 127) / 128, (long long)sms * 8);
+    if (p->views_per_chunk == 1) {
+        // one launch: leading CTAs clear the rows of voxels nothing hit, the rest gather (plain stores)
+        a.zero_blocks = (int)zero_blocks;
         ScopedKernelTimer timer(1, st);
-        if (fused) backward_gather_kernel<true><<<blocks, 256, 0, st>>>(a);
-        else backward_gather_kernel<false><<<blocks, 256, 0, st>>>(a);
+        if (fused) backward_gather_kernel<true, false><<<zero_blocks + gather_blocks, 128, 0, st>>>(a);
+        else backward_gather_kernel<false, false><<<zero_blocks + gather_blocks, 128, 0, st>>>(a);
+    } else {
+        a.zero_blocks = 0;
+        backward_zero_kernel<<<zero_blocks, 128, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        ScopedKernelTimer timer(1, st);
+        if (fused) backward_gather_kernel<true, true><<<gather_blocks, 128, 0, st>>>(a);
+        else backward_gather_kernel<false, true><<<gather_blocks, 128, 0, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
@@ -1249,7 +1389,7 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
 
 extern "C" {
 
-const char *spsg_version(void) { return "spsg_raycast_b200 0.2 (sm_100a)"; }
+const char *spsg_version(void) { return "spsg_raycast_b200 0.3 (sm_100a)"; }
 const char *spsg_last_error(void) { return g_err; }
 
 void spsg_timing_enable(int on) {

@@ -71,7 +71,7 @@ class FusedRaycastLossFunction(Function):
         if getattr(m, "loss_out", None) is None:
             m.loss_out = torch.zeros(N.SPSG_LOSS_OUT_FLOATS, device=dev)
         with torch.cuda.device(dev):
-            ws = rc.workspace(dev, N.workspace_bytes(p))
+            ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
             N.check(N.lib.spsg_raycast_forward_loss(
                 ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
                 N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
@@ -97,7 +97,7 @@ class FusedRaycastLossFunction(Function):
         dev = m.image_depth.device
         scale = grad_total.to(torch.float32).contiguous()
         with torch.cuda.device(dev):
-            ws = rc.workspace(dev, N.workspace_bytes(p))
+            ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
             N.check(N.lib.spsg_raycast_backward_loss(
                 ctypes.byref(p), N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_semantic),
                 ctypes.byref(tg), N.ptr(m.loss_out), N.ptr(scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),

@@ -13,6 +13,7 @@ Same four entry points, positional tensors, in-place outputs and error behaviour
     raycast_occ(occ3d, occ2d, viewMatrixInv, intrinsicParams, opts)
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -34,14 +35,22 @@ def _check_dtype(t, dtype, name):
         raise RuntimeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
 
 
-def workspace(device, nbytes):
-    """Per-device scratch tensor, grown on demand (the C ABI never allocates)."""
-    key = (device.type, device.index)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
+def workspace(device, nbytes, owner=None):
+    """Scratch tensor of one raycaster (keyed by its ``sparse_mapping`` buffer), grown on demand; the C ABI never
+    allocates.  The forward leaves the backward's work list in it, so -- like the reference's ``mapping3dto2d``
+    tables (raycast_rgbd.py:29-32) -- it belongs to the module whose buffers the call pair uses.  Entries die with
+    their owner's storage."""
+    key = (device.type, device.index, None if owner is None else owner.data_ptr())
+    entry = _workspaces.get(key)
+    if entry is not None and entry[1] is not None and entry[1]() is None and owner is not None:
+        entry = None  # the buffer that owned this address is gone; the address now belongs to a new raycaster
+    if entry is None or entry[0].numel() < nbytes:
+        for k in [k for k, e in _workspaces.items() if e[1] is not None and e[1]() is None]:
+            del _workspaces[k]
         ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+        entry = (ws, None if owner is None else weakref.ref(owner.untyped_storage()))
+        _workspaces[key] = entry
+    return entry[0]
 
 
 def _stream(device):
@@ -109,7 +118,7 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
     dev = vals_sdf.device
     with torch.cuda.device(dev):
         nbytes = N.workspace_bytes(p)
-        ws = workspace(dev, nbytes)
+        ws = workspace(dev, nbytes, sparse_mapping)
         fn = N.lib.spsg_raycast_forward_indexed if build_index else N.lib.spsg_raycast_forward
         N.check(fn(ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
                    N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(viewMatrixInv), N.ptr(intrinsicParams),
@@ -137,7 +146,7 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                       max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n)
     dev = grad_color.device
     with torch.cuda.device(dev):
-        ws = workspace(dev, N.workspace_bytes(p))
+        ws = workspace(dev, N.workspace_bytes(p), sparse_mapping)
         N.check(N.lib.spsg_raycast_backward(ctypes.byref(p), N.ptr(grad_color), N.ptr(grad_depth), N.ptr(grad_normal),
                                             N.ptr(grad_semantic), N.ptr(sparse_mapping), N.ptr(mapping3dto2d),
                                             N.ptr(mapping3dto2d_num), N.ptr(d_color), N.ptr(d_depth),

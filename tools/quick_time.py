@@ -45,6 +45,12 @@ def run(B, F, flags_list=(0, 1, 2, 3)):
         torch.autograd.backward(o, grads)
     us = timeit(fb)
     print("mine fwd+bwd (autograd): %.1f us  %.2f Grays/s" % (us, rays / us / 1e3))
+    from spsg_b200 import _native as N
+    N.timing_read(0); N.timing_read(1); N.timing_enable(True)
+    for _ in range(20): fb()
+    torch.cuda.synchronize(); N.timing_enable(False)
+    f_ms, f_n = N.timing_read(0); g_ms, g_n = N.timing_read(1)
+    print("kernel device time: raycast_forward %.1f us, backward_gather %.1f us" % (f_ms / f_n * 1e3, g_ms / g_n * 1e3))
     from spsg_b200 import raycast_rgbd_cuda as rc
     dims = [B, 64, 64, 128, n]
     def bwd():
