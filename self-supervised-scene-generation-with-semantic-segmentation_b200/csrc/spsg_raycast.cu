@@ -40,12 +40,9 @@ constexpr float kBoxEps = 1.0f / 64.0f;  // shrink of skip regions; >> every fp3
 constexpr float kFracGuard = 1.0f / 256.0f;  // fast corner path needs frac(p) in [guard, 1-guard]
 constexpr int kMaxFastDim = 8192;        // fast corner path proven for coordinates < 2^13
 constexpr int kLossSlots = 64;           // copies of the loss accumulators (spreads atomic contention)
-constexpr int kMaxSmemBlockMap = 32768;  // block maps up to this size are staged in shared memory
 
 // block map byte = kind << 3 | level; level k >= 1: the aligned region of edge 2^(k+1) voxels around the block
 enum { kKindSurface = 0, kKindEmpty = 1, kKindPos = 2, kKindNeg = 3 };
-// cell class byte
-enum { kCellInvalid = 0, kCellPos = 1, kCellNeg = 2, kCellMixed = 3 };
 
 thread_local char g_err[512] = "";
 
@@ -95,11 +92,15 @@ struct Layout {
     int nbx, nby, nbz;              // 4^3 blocks per axis
     size_t bpc;                     // block-map bytes per chunk (nbx*nby*nbz rounded up to 16)
     size_t dense_off, dense_bytes;  // f32 [B][Dz][Dy][Dx], NaN = absent
-    size_t cmap_off, cmap_bytes;    // u8  [B][Dz][Dy][Dx] class of the sample cell whose corner (0,0,0) is the voxel
+    int wpr;                        // 32-cell words per x row of the cell-class bit planes
+    size_t vpc;                     // uint2 words per chunk of the cell-class map (Dz*Dy*wpr rounded up to even)
+    size_t vbit_off, vbit_bytes;    // uint2 [B][vpc]: bit x of (.x, .y) = class of the sample cell whose corner (0,0,0)
+                                    // is the voxel: 00 invalid, 10 positive, 01 negative, 11 mixed
     size_t bmap_off, bmap_bytes;    // u8  [B][bpc] block map
     size_t zero_off, zero_bytes;    // everything below is cleared by the fill kernel of every forward
     size_t marks_off, marks_bytes;  // u8  [3][B][bpc]: block holds a positive / negative / mixed cell
     size_t head_off;                // int32 list counter (256 B)
+    size_t tiles_off, tiles_bytes;  // int32 [B] dynamic tile counters of the forward
     size_t loss_off, loss_bytes;    // double[kLossSlots][8] loss accumulators
     size_t list_off, list_bytes;    // int2 (voxel, image) per (voxel, view) pair that received a pixel
     size_t hits_off, hits_bytes;    // optional int32 per-pixel hit voxel
@@ -118,9 +119,11 @@ Layout make_layout(const spsg_raycast_params *p) {
     L.dense_off = off;
     L.dense_bytes = align_up(cells * sizeof(float), 256);
     off += L.dense_bytes;
-    L.cmap_off = off;
-    L.cmap_bytes = align_up(cells, 256);
-    off += L.cmap_bytes;
+    L.wpr = (p->dimx + 31) / 32;
+    L.vpc = align_up((size_t)p->dimz * p->dimy * L.wpr, 2);
+    L.vbit_off = off;
+    L.vbit_bytes = align_up((size_t)p->num_chunks * L.vpc * sizeof(uint2), 256);
+    off += L.vbit_bytes;
     L.bmap_off = off;
     L.bmap_bytes = align_up((size_t)p->num_chunks * L.bpc, 256);
     off += L.bmap_bytes;
@@ -130,6 +133,9 @@ Layout make_layout(const spsg_raycast_params *p) {
     off += L.marks_bytes;
     L.head_off = off;
     off += 256;
+    L.tiles_off = off;
+    L.tiles_bytes = align_up((size_t)p->num_chunks * sizeof(int32_t), 256);
+    off += L.tiles_bytes;
     L.loss_off = off;
     L.loss_bytes = align_up((size_t)kLossSlots * 8 * sizeof(double), 256);
     off += L.loss_bytes;
@@ -247,6 +253,7 @@ struct Volume {
     const float *__restrict__ sdf;      // vals_sdf
     const float *__restrict__ dense;    // this chunk's slice of the dense SDF brick (NaN = absent)
     int dimx, dimy, dimz;
+    float guard;                        // fast corner path needs frac(p) in [guard, 1 - guard] (see frac_guard)
 };
 
 __device__ __forceinline__ bool in_grid(const Volume &v, int x, int y, int z) {
@@ -290,14 +297,19 @@ __device__ __noinline__ bool sample_sdf_exact(const Volume &v, float px, float p
     return true;
 }
 
-// Same result as sample_sdf_exact.  Fast path: when frac(p) is at least kFracGuard away from 0 and 1 on every
-// axis and 0 <= floor(p), floor(p)+1 < dim, the reference's rounded corner coordinates are exactly floor(p) and
-// floor(p)+1 ("corner coordinates"), and the 8 values come straight from the dense brick where an
-// absent corner is NaN, which the fma chain propagates: valid <=> dist is not NaN.  (A present voxel holding NaN,
-// or inf * 0, makes the reference's sample "valid with NaN distance", which can never satisfy the sign test
-// and leaves the same march state as an invalid sample -- observationally identical.)
-__device__ __forceinline__ bool frac_guard_ok(float wx, float wy, float wz) {
-    return fminf(wx, fminf(wy, wz)) >= kFracGuard && fmaxf(wx, fmaxf(wy, wz)) <= 1.0f - kFracGuard;
+// Same result as sample_sdf_exact.  Fast path: when frac(p) is at least `guard` away from 0 and 1 on every axis and
+// 0 <= floor(p), floor(p)+1 < dim, the reference's rounded corner coordinates are exactly floor(p) and floor(p)+1
+// ("corner coordinates"), and the 8 values come straight from the dense brick where an absent corner is
+// NaN, which the fma chain propagates: valid <=> dist is not NaN.  (A present voxel holding NaN, or inf * 0, makes the
+// reference's sample "valid with NaN distance", which can never satisfy the sign test and leaves the same march state
+// as an invalid sample -- observationally identical.)
+//
+// The guard.  For p >= 1 (below 2^23) q = p - 0.5 and q + 0.5 = p are exact in fp32, so corner 0 is trunc(p) = floor(p)
+// whatever frac(p) is; corner 1 = trunc(fl(fl(q + 1) + 0.5)) accumulates at most two roundings of at most ulp(2p), so it
+// is floor(p) + 1 as soon as frac(p) is 8 ulp(p) away from 0 and 1: guard = 8 ulp(largest coordinate).  In the first
+// voxel layer (p < 1 on some axis) q is negative and p - 0.5 is no longer exact: there the guard is kFracGuard.
+__device__ __forceinline__ float frac_guard(float guard, int ix, int iy, int iz) {
+    return (((ix - 1) | (iy - 1) | (iz - 1)) < 0) ? kFracGuard : guard;
 }
 
 __device__ __forceinline__ float sample_dense(const Volume &v, int ix, int iy, int iz, float wx, float wy, float wz) {
@@ -312,8 +324,9 @@ __device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float 
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = __fadd_rn(px, -fx), wy = __fadd_rn(py, -fy), wz = __fadd_rn(pz, -fz);
     const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
-    const bool fast = fast_ok && frac_guard_ok(wx, wy, wz) && (ix | iy | iz) >= 0 && ix + 1 < v.dimx &&
-                      iy + 1 < v.dimy && iz + 1 < v.dimz;
+    const float g = frac_guard(v.guard, ix, iy, iz);
+    const bool fast = fast_ok && fminf(wx, fminf(wy, wz)) >= g && fmaxf(wx, fmaxf(wy, wz)) <= 1.0f - g &&
+                      (ix | iy | iz) >= 0 && ix + 1 < v.dimx && iy + 1 < v.dimy && iz + 1 < v.dimz;
     if (fast) {
         dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
         return dist == dist;
@@ -377,32 +390,28 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
 //            >= 0, they sum to ~1 so one is >= 1/8, and products with values above kTiny cannot underflow;
 //   negative likewise with all corners in (-kHuge, -kTiny): value < 0;
 //   mixed    all present, anything else: the value has to be computed.
-// One byte per cell; one warp per 32 cells of an x row.  Also marks, per 4^3 block, whether it holds a positive, a
-// negative or a mixed cell (three byte planes, plain stores of 1: a benign race).
+// Two bit planes per 32 cells of an x row (see Layout); one warp per word.  Also marks, per 4^3 block, whether it
+// holds a positive, a negative or a mixed cell (three byte planes, plain stores of 1: a benign race).
+// grid = (ceil(Dy*wpr / 8), Dz, B), block = 256.
 constexpr float kTiny = 1e-30f, kHuge = 3e38f;
 
-__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint8_t *__restrict__ cmap,
-                                                         uint8_t *__restrict__ marks, size_t plane_stride,
-                                                         int num_chunks, int dimz, int dimy, int dimx, int wpr, int nbz,
-                                                         int nby, int nbx, size_t bpc) {
+__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
+                                                         size_t vpc, uint8_t *__restrict__ marks, size_t plane_stride,
+                                                         int dimz, int dimy, int dimx, int wpr, int nby, int nbx,
+                                                         size_t bpc) {
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long rows = (long long)num_chunks * dimz * dimy;
-    if (warp >= rows * wpr) return;
-    const int xw = (int)(warp % wpr);
-    long long row = warp / wpr;
-    const int y = (int)(row % dimy); row /= dimy;
-    const int z = (int)(row % dimz);
-    const int chunk = (int)(row / dimz);
-    const size_t cells = (size_t)dimz * dimy * dimx;
-    const float *__restrict__ base = dense + (size_t)chunk * cells;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);  // (y, xw) of this warp's word
+    if (w >= dimy * wpr) return;
+    const int y = w / wpr, xw = w - y * wpr;
+    const int z = blockIdx.y, chunk = blockIdx.z;
+    const float *__restrict__ base = dense + (size_t)chunk * dimz * dimy * dimx;
     const bool inner = (y + 1 < dimy) && (z + 1 < dimz);  // warp-uniform
-    const size_t o00 = ((size_t)z * dimy + y) * dimx;
     // per x column (x, y..y+1, z..z+1): all present / all positive class / all negative class
     bool col = false, pos = false, neg = false, coln = false, posn = false, negn = false;
-    const int x = xw * 32 + lane;
     if (inner) {
-        const size_t o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx, o11 = o01 + dimx;
+        const size_t o00 = ((size_t)z * dimy + y) * dimx, o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx,
+                     o11 = o01 + dimx;
+        const int x = xw * 32 + lane;
         if (x < dimx) {
             const float a = __ldg(base + o00 + x), b = __ldg(base + o10 + x), c = __ldg(base + o01 + x),
                         d = __ldg(base + o11 + x);
@@ -428,11 +437,7 @@ __global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict
     const unsigned v = SPSG_PAIR(cb, cbn), vp = SPSG_PAIR(pb, pbn), vn = SPSG_PAIR(nb, nbn);
 #undef SPSG_PAIR
     const unsigned vm = v & ~vp & ~vn;
-    if (x < dimx) {
-        const unsigned bit = 1u << lane;
-        const uint8_t cls = !(v & bit) ? kCellInvalid : (vp & bit) ? kCellPos : (vn & bit) ? kCellNeg : kCellMixed;
-        cmap[(size_t)chunk * cells + o00 + x] = cls;
-    }
+    if (lane == 0) vbits[(size_t)chunk * vpc + ((size_t)z * dimy + y) * wpr + xw] = make_uint2(v & ~vn, v & ~vp);
     if (lane < 24) {  // lanes 0-7: positive plane, 8-15: negative, 16-23: mixed; 4 cells of one block per lane
         const int plane = lane >> 3, g = lane & 7;
         const unsigned m = plane == 0 ? vp : plane == 1 ? vn : vm;
@@ -501,6 +506,21 @@ __global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restric
 // forward
 // ---------------------------------------------------------------------------------------------
 
+#ifdef SPSG_STATS
+// development build only (-DSPSG_STATS): event counters of the march, read back with spsg_debug_stats()
+__device__ unsigned long long g_stats[48];
+#define STAT_MAX(k, v) atomicMax(&g_stats[k], (unsigned long long)(v))
+#define STAT_ADD(k, v) atomicAdd(&g_stats[k], (unsigned long long)(v))
+#if SPSG_STATS == 1
+#define EVT_ADD(k, v) STAT_ADD(k, v)  // per-event counters (slow: perturbs timing)
+#else
+#define EVT_ADD(k, v)
+#endif
+#else
+#define STAT_ADD(k, v)
+#define STAT_MAX(k, v)
+#endif
+
 struct LossArgs {
     const float *target_depth, *target_color, *weight_color;
     const uint8_t *target_label;
@@ -516,9 +536,12 @@ struct ForwardArgs {
     float *image_color, *image_depth, *image_normal, *image_semantic;
     int32_t *mapping3dto2d, *mapping3dto2d_num;
     const float *dense;
-    const uint8_t *cmap, *bmap;
-    size_t bpc;
-    int bmap_in_smem;
+    const uint2 *vbits;   // [B][vpc]
+    const uint8_t *bmap;  // [B][bpc]
+    size_t vpc, bpc;
+    int wpr;
+    int maps_in_smem;
+    int32_t *tile_counter;  // [B], zeroed per call
     int32_t *list_count;
     int2 *list;
     int32_t *hits;
@@ -526,15 +549,23 @@ struct ForwardArgs {
     float depth_min, depth_max, thresh, inc;
     int dimx, dimy, dimz;
     int nbx, nby, nbz;
-    int views, max_pixels;
+    int num_chunks, views, max_pixels;
     long long num_locs;
     unsigned flags;
     int vec_ok;  // image rows 16-byte aligned: float4 write-out allowed
+    float guard; // see frac_guard
     LossArgs loss;
 };
 
-constexpr int kTileW = 16, kTileH = 8;  // pixels per CTA: 4 warps of 8x4 pixels
+constexpr int kTileW = 16, kTileH = 8;  // pixels per CTA of the occupancy kernel: 4 warps of 8x4 pixels
 constexpr int kTilePix = kTileW * kTileH;
+
+constexpr int kWarpW = 8, kWarpH = 4;                   // pixels per warp tile
+constexpr int kFwdWarps = 24;                           // warps of the persistent forward CTA (one CTA per SM)
+constexpr int kFwdThreads = kFwdWarps * 32;
+constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
+constexpr size_t kFwdSmemFixed = 128 + (size_t)kFwdWarps * kStageFloats * sizeof(float);
+constexpr size_t kFwdSmemMax = 232448;                  // 227 KB opt-in limit per CTA
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -542,7 +573,31 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-constexpr int kWarpW = 8, kWarpH = 4;  // pixels per warp
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!done);
+}
 
 // Write-out of one channel group of a warp's 8x4 pixel tile: smem [kWarpH][kWarpW*C] -> global rows, by the warp.
 template <int C>
@@ -567,71 +622,123 @@ __device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, flo
     }
 }
 
-// One thread per ray.  kernel.cu:265-297 (init + ray), :190-263 (march), :166-187 (regula falsi),
-// :215-249 (hit write-out + voxel->pixel registration); kLoss adds the 2D losses (train.py:635-638,
-// loss.py:246-257, train.py:744-746) to the epilogue.
+// Persistent forward: one CTA per SM, one thread per ray, one 8x4-pixel tile per warp at a time.
+// kernel.cu:265-297 (init + ray), :190-263 (march), :166-187 (regula falsi), :215-249 (hit write-out + voxel->pixel
+// registration); kLoss adds the 2D losses (train.py:635-638, loss.py:246-257, train.py:744-746) to the epilogue.
+// CTA i works on chunk i % B (then i % B + gridDim, ...): the chunk's cell-class bit planes and block map are pulled
+// into shared memory once by TMA bulk copies, so the march's "does this sample need arithmetic" lookups never leave
+// the SM; tiles of the chunk's images are dealt to warps first statically, then from a global counter.
 template <bool kLoss>
-__global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const ForwardArgs a) {
-    // per-warp staging of the rendered tile (warps retire independently)
-    __shared__ __align__(16) float s_sem_all[kTilePix * 14];
-    __shared__ __align__(16) float s_col_all[kTilePix * 3];
-    __shared__ __align__(16) float s_nrm_all[kTilePix * 3];
-    __shared__ __align__(16) float s_dep_all[kTilePix];
-    extern __shared__ __align__(16) uint8_t s_bmap[];  // this chunk's block map (when it fits)
-
+__global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const ForwardArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx = (warp & 1) * 8 + (lane & 7), ty = (warp >> 1) * 4 + (lane >> 3);
-    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-    const unsigned ux = x0 + tx, uy = y0 + ty;
-    const int img = blockIdx.z;
-    const bool active = ux < (unsigned)a.width && uy < (unsigned)a.height;
-    const int chunk = img / a.views, view = img - chunk * a.views;
-    const unsigned pix = uy * a.width + ux;
-    const size_t gpix = (size_t)img * a.width * a.height + pix;
+    float *stage = reinterpret_cast<float *>(smem + 128) + warp * kStageFloats;
+    uint2 *s_vbits = reinterpret_cast<uint2 *>(smem + kFwdSmemFixed);
+    uint8_t *s_bmap = reinterpret_cast<uint8_t *>(s_vbits + a.vpc);
+    const unsigned kFull = 0xffffffffu;
+    const float kInf = CUDART_INF_F;
 
-    const uint8_t *__restrict__ gbmap = a.bmap + (size_t)chunk * a.bpc;
-    if (a.bmap_in_smem) {  // issue the copy first: its latency hides behind the ray setup
-        const uint4 *src = reinterpret_cast<const uint4 *>(gbmap);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_bmap);
-        for (int i = threadIdx.x; i < (int)(a.bpc >> 4); i += kTilePix) dst[i] = __ldg(src + i);
+    if (a.maps_in_smem) {
+        if (threadIdx.x == 0) mbar_init(mbar, 1);
+        __syncthreads();
     }
+    unsigned phase = 0;
 
-    int hit = -1;
-    float depth = 0.0f;
-
-    // Lanes outside the image run the same loops below with an exhausted ray.
-    const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, active ? ux : 0u,
-                            active ? uy : 0u, a.depth_min, a.depth_max);
     const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
-    Volume v;
-    v.index = a.sparse_mapping + (size_t)chunk * cells;
-    v.sdf = a.vals_sdf;
-    v.dense = a.dense + (size_t)chunk * cells;
-    v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
-    const uint8_t *__restrict__ cmap = a.cmap + (size_t)chunk * cells;
     const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
     const bool skip = !(a.flags & SPSG_FLAG_NO_BRICK_SKIP);
     const bool fast_ok = max(a.dimx, max(a.dimy, a.dimz)) <= kMaxFastDim;
-    const float kInf = CUDART_INF_F;
-    // approximate reciprocals are only used to size jumps; every margin below dwarfs their error
-    const float invx = r.dx != 0.0f ? rcp_approx(r.dx) : 0.0f, invy = r.dy != 0.0f ? rcp_approx(r.dy) : 0.0f,
-                invz = r.dz != 0.0f ? rcp_approx(r.dz) : 0.0f;
-    Stepper step;
-    step.init(a.inc);
+    const bool skip_ok = skip && fast_ok;
+    // warp tiles are numbered so that the four tiles of a 16x8 pixel block are consecutive
+    const int tiles_x = (a.width + kWarpW - 1) / kWarpW, tiles_y = (a.height + kWarpH - 1) / kWarpH;
+    const int blocks_x = (tiles_x + 1) >> 1, blocks_y = (tiles_y + 1) >> 1;
+    const int tiles_per_image = blocks_x * blocks_y * 4;
+    const int total_tiles = tiles_per_image * a.views;
 
-    float ray = r.t0, t_end = active ? r.t1 : -kInf;
-    // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (Stepper): cap j so that this
-    // drift stays below kBoxEps / 4, far inside the kBoxEps the skip regions are shrunk by.
-    int jump_cap = 1 << 22;
-    {
-        const float top = fmaxf(fabsf(r.t1), 1.0f);
-        const float ulp = __uint_as_float(__float_as_uint(top) & 0x7f800000u) * 1.1920928955078125e-07f;
-        const float cap = (0.5f * kBoxEps) / ulp;
-        jump_cap = cap < 4194304.0f ? max(1, __float2int_rd(cap)) : (1 << 22);
-    }
-    if (clip && active) {
-        // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
-        float tin = -kInf, tout = kInf;
+    for (int chunk = blockIdx.x % a.num_chunks; chunk < a.num_chunks; chunk += gridDim.x) {
+        if (a.maps_in_smem && threadIdx.x == 0) {
+            const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2)), bm_bytes = (unsigned)a.bpc;
+            mbar_expect_tx(mbar, vb_bytes + bm_bytes);
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(a.vbits + (size_t)chunk * a.vpc);
+            uint8_t *dst = reinterpret_cast<uint8_t *>(s_vbits);
+            for (unsigned o = 0; o < vb_bytes; o += 32768u) bulk_copy_g2s(dst + o, src + o, min(32768u, vb_bytes - o), mbar);
+            bulk_copy_g2s(s_bmap, a.bmap + (size_t)chunk * a.bpc, bm_bytes, mbar);
+        }
+        bool maps_ready = !a.maps_in_smem;
+        const uint2 *vbits = a.maps_in_smem ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
+        const uint8_t *bmap = a.maps_in_smem ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
+        Volume v;
+        v.index = a.sparse_mapping + (size_t)chunk * cells;
+        v.sdf = a.vals_sdf;
+        v.dense = a.dense + (size_t)chunk * cells;
+        v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
+        v.guard = a.guard;
+
+        // CTAs that share this chunk: ranks 0..group-1.  First round static and contiguous per CTA, then dynamic.
+        const int nb = a.num_chunks;
+        const int group = ((int)gridDim.x - 1 - (int)(blockIdx.x % nb)) / nb + 1, rank = blockIdx.x / nb;
+        const int static_tiles = min(total_tiles, group * kFwdWarps);
+        const int per = static_tiles / group, extra = static_tiles - per * group;
+        const int my_first = rank * per + min(rank, extra), my_count = per + (rank < extra ? 1 : 0);
+        int tile = warp < my_count ? my_first + warp : total_tiles;
+        int32_t *counter = a.tile_counter + chunk;
+        if (tile >= total_tiles && static_tiles < total_tiles) {
+            int t = 0;
+            if (lane == 0) t = static_tiles + atomicAdd(counter, 1);
+            tile = __shfl_sync(kFull, t, 0);
+        }
+
+        while (tile < total_tiles) {
+            int next = total_tiles;
+            if (lane == 0 && static_tiles < total_tiles) next = static_tiles + atomicAdd(counter, 1);  // prefetched
+
+            const int view = tile / tiles_per_image, tt = tile - view * tiles_per_image;
+            const int blk = tt >> 2, sub = tt & 3;
+            const int by = blk / blocks_x, bx = blk - by * blocks_x;
+            const int wx0 = (bx * 2 + (sub & 1)) * kWarpW, wy0 = (by * 2 + (sub >> 1)) * kWarpH;
+            const int img = chunk * a.views + view;
+            if (wx0 < a.width && wy0 < a.height) {
+                const unsigned ux = wx0 + (lane & 7), uy = wy0 + (lane >> 3);
+                const bool active = ux < (unsigned)a.width && uy < (unsigned)a.height;
+                const unsigned pix = uy * a.width + ux;
+                const size_t gpix = (size_t)img * a.width * a.height + pix;
+
+                int hit = -1;
+                float depth = 0.0f;
+#ifdef SPSG_STATS
+                const long long clk0 = clock64();
+                long long clk_march = 0, clk_refine = 0;
+                int my_iters = 0;
+#endif
+
+                // Lanes outside the image run the same loops below with an exhausted ray.
+                const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4,
+                                        active ? ux : 0u, active ? uy : 0u, a.depth_min, a.depth_max);
+                // approximate reciprocals are only used to size jumps; every margin below dwarfs their error
+                const float invx = r.dx != 0.0f ? rcp_approx(r.dx) : 0.0f, invy = r.dy != 0.0f ? rcp_approx(r.dy) : 0.0f,
+                            invz = r.dz != 0.0f ? rcp_approx(r.dz) : 0.0f;
+                // exit-plane constants of the region jumps: t = (face -+ kBoxEps - cam) / dir, +inf for an axis-parallel ray
+                const float kx = r.dx != 0.0f ? ((r.dx > 0.0f ? -kBoxEps : kBoxEps) - r.camx) * invx : kInf;
+                const float ky = r.dy != 0.0f ? ((r.dy > 0.0f ? -kBoxEps : kBoxEps) - r.camy) * invy : kInf;
+                const float kz = r.dz != 0.0f ? ((r.dz > 0.0f ? -kBoxEps : kBoxEps) - r.camz) * invz : kInf;
+                const int sxm = r.dx > 0.0f ? -1 : 0, sym = r.dy > 0.0f ? -1 : 0, szm = r.dz > 0.0f ? -1 : 0;
+                Stepper step;
+                step.init(a.inc);
+
+                float ray = r.t0, t_end = active ? r.t1 : -kInf;
+                // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (Stepper): cap j so that
+                // this drift stays below kBoxEps / 4, far inside the kBoxEps the skip regions are shrunk by.
+                int jump_cap = 1 << 22;
+                {
+                    const float top = fmaxf(fabsf(r.t1), 1.0f);
+                    const float ulp = __uint_as_float(__float_as_uint(top) & 0x7f800000u) * 1.1920928955078125e-07f;
+                    const float cap = (0.5f * kBoxEps) / ulp;
+                    jump_cap = cap < 4194304.0f ? max(1, __float2int_rd(cap)) : (1 << 22);
+                }
+                if (clip && active) {
+                    // Samples are valid only for p in (0, dim-1) on every axis (all 8 corners inside the grid).
+                    float tin = -kInf, tout = kInf;
 #define SPSG_SLAB(o, d, inv, lo, hi)                                        \
     if ((d) != 0.0f) {                                                      \
         const float ta_ = ((lo) - (o)) * (inv), tb_ = ((hi) - (o)) * (inv); \
@@ -641,276 +748,329 @@ __global__ void __launch_bounds__(kTilePix, 6) raycast_forward_kernel(const Forw
         tin = kInf;                                                         \
         tout = -kInf;                                                       \
     }
-        SPSG_SLAB(r.camx, r.dx, invx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps)
-        SPSG_SLAB(r.camy, r.dy, invy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps)
-        SPSG_SLAB(r.camz, r.dz, invz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps)
+                    SPSG_SLAB(r.camx, r.dx, invx, -kBoxEps, (float)(a.dimx - 1) + kBoxEps)
+                    SPSG_SLAB(r.camy, r.dy, invy, -kBoxEps, (float)(a.dimy - 1) + kBoxEps)
+                    SPSG_SLAB(r.camz, r.dz, invz, -kBoxEps, (float)(a.dimz - 1) + kBoxEps)
 #undef SPSG_SLAB
-        const float margin = 0.0625f;
-        if (!(tin <= tout)) {
-            t_end = -kInf;  // misses the grid: nothing to march
-        } else {
-            t_end = fminf(t_end, tout + margin);
-            // jump to (at most) the last sample before tin - margin
-            while (ray < tin - margin - a.inc && ray < t_end) {
-                const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, jump_cap));
-                ray = step.advance(ray, want);
-            }
-        }
-    }
-
-    if (a.bmap_in_smem) __syncthreads();  // the block map copy has landed
-    const uint8_t *bmap = a.bmap_in_smem ? s_bmap : gbmap;
-
-    // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the sign the
-    // cell class guarantees; the value is computed if and when a crossing needs it.
-    float last_sdf = 0.0f, last_alpha = 0.0f;
-    bool last_ok = false, last_lazy = false;
-    float dist = 0.0f;
-    enum { kMarch = 0, kCross = 1, kDone = 2 };
-    int state = kMarch;
-    const unsigned kFull = 0xffffffffu;
-
-    for (;;) {
-        // ---- march.  The loop is warp-synchronous: all lanes take part in every vote and every iteration handles one
-        // event per marching lane, so diverged lanes re-join at the bottom of each iteration instead of running their
-        // iterations one group after the other.  An event is either a jump over samples whose outcome is known from
-        // the block map, or one sample.
-        while (__any_sync(kFull, state == kMarch)) {
-            if (state == kMarch) {
-                if (!(ray < t_end)) {  // kernel.cu:200
-                    state = kDone;
-                } else {
-                    enum { kActExact = 0, kActDense = 1, kActInvalid = 2, kActSign = 3, kActJumpEmpty = 4, kActJumpSame = 5 };
-                    int act = kActExact, nadv = 1;
-                    float sgn = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f;
-                    int ix = 0, iy = 0, iz = 0;
-                    const float px = __fmaf_rn(r.dx, ray, r.camx), py = __fmaf_rn(r.dy, ray, r.camy),
-                                pz = __fmaf_rn(r.dz, ray, r.camz);
-                    if (skip && fast_ok) {
-                        const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-                        ix = __float2int_rz(fx); iy = __float2int_rz(fy); iz = __float2int_rz(fz);
-                        if ((unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
-                            (unsigned)iz < (unsigned)a.dimz) {
-                            const int b = bmap[((iz >> kFineLog2) * a.nby + (iy >> kFineLog2)) * a.nbx + (ix >> kFineLog2)];
-                            // the cell class is fetched alongside (independent address): one memory round trip per event
-                            const int cls = cmap[((size_t)iz * a.dimy + iy) * a.dimx + ix];
-                            wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
-                            if (b != 0) {
-                                // p is inside an aligned uniform region of edge `size`.  If it is at least kBoxEps inside
-                                // on every axis, corner (0,0,0) of this sample and of every later one up to the region's
-                                // exit lies in the region.
-                                const int kind = b >> 3, size = 2 << (b & 7), mask = ~(size - 1);
-                                const float lox = (float)(ix & mask) + kBoxEps, hix = (float)((ix & mask) + size) - kBoxEps;
-                                const float loy = (float)(iy & mask) + kBoxEps, hiy = (float)((iy & mask) + size) - kBoxEps;
-                                const float loz = (float)(iz & mask) + kBoxEps, hiz = (float)((iz & mask) + size) - kBoxEps;
-                                // a sign-uniform region cannot be jumped while the last valid sample has the other sign:
-                                // its first valid sample would be a crossing
-                                const bool opposite = last_ok && ((kind == kKindPos && last_sdf < 0.0f) ||
-                                                                  (kind == kKindNeg && last_sdf > 0.0f));
-                                if (!opposite && px >= lox && px <= hix && py >= loy && py <= hiy && pz >= loz && pz <= hiz) {
-                                    const float tx_ = r.dx != 0.0f ? ((r.dx > 0.0f ? hix : lox) - r.camx) * invx : kInf;
-                                    const float ty_ = r.dy != 0.0f ? ((r.dy > 0.0f ? hiy : loy) - r.camy) * invy : kInf;
-                                    const float tz_ = r.dz != 0.0f ? ((r.dz > 0.0f ? hiz : loz) - r.camz) * invz : kInf;
-                                    const float tout = fminf(tx_, fminf(ty_, tz_));
-                                    // steps to the first sample beyond the region's exit
-                                    int n = 1;
-                                    if (tout > ray) n = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, jump_cap));
-                                    if (kind == kKindEmpty) {
-                                        // every sample before that one is invalid (kernel.cu:131,259)
-                                        act = kActJumpEmpty; nadv = n;
-                                    } else if (n >= 2) {
-                                        // Samples up to the last one inside are invalid or share the region's sign, and
-                                        // so does the last valid one before them: no crossing.  Land on the last one
-                                        // inside; it is classified by its own cell and leaves the march state exactly as
-                                        // the reference's sample-by-sample walk would.
-                                        act = kActJumpSame; nadv = n - 1;
-                                    }
-                                }
-                            }
-                            if (act == kActExact && frac_guard_ok(wx, wy, wz)) {
-                                // One sample, decided by its own cell.  With frac(p) clear of the cell faces the
-                                // reference's corners are exactly floor(p) + {0,1}; the cell's class says whether all 8
-                                // are present and whether they share a sign.
-                                if (cls == kCellInvalid) {
-                                    act = kActInvalid;
-                                } else {
-                                    act = kActDense;
-                                    if (cls != kCellMixed) {
-                                        sgn = cls == kCellPos ? 1.0f : -1.0f;
-                                        // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN)
-                                        if (!(last_ok && __fmul_rn(last_sdf, sgn) < 0.0f)) act = kActSign;
-                                    }
-                                }
-                            }
+                    const float margin = 0.0625f;
+                    if (!(tin <= tout)) {
+                        t_end = -kInf;  // misses the grid: nothing to march
+                    } else {
+                        t_end = fminf(t_end, tout + margin);
+                        // jump to (at most) the last sample before tin - margin
+                        while (ray < tin - margin - a.inc && ray < t_end) {
+                            const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, jump_cap));
+                            ray = step.advance(ray, want);
                         }
                     }
-                    if (act <= kActDense) {
-                        bool valid;
-                        if (act == kActDense) {
-                            dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
-                            valid = dist == dist;
-                        } else {
-                            valid = sample_sdf(v, fast_ok, px, py, pz, dist);  // the reference's exact corner arithmetic
-                        }
-                        if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
-                            state = kCross;
-                        } else if (valid) {
-                            last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
-                        } else {
-                            last_ok = false;  // :259
-                        }
-                    } else if (act == kActSign) {
-                        last_sdf = sgn; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
-                    } else if (act != kActJumpSame) {
-                        last_ok = false;  // :259 (invalid sample, or a run of them)
-                    }
-                    if (state == kMarch) ray = (nadv == 1) ? __fadd_rn(ray, a.inc) : step.advance(ray, nadv);  // :257,:260
                 }
-            }
-        }
-        // ---- refinement round: every lane is either waiting with a crossing or finished
-        if (!__any_sync(kFull, state == kCross)) break;
-        if (state == kCross) {
-            if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
-                float dl = last_sdf;
-                if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
-                               __fmaf_rn(r.dz, last_alpha, r.camz), dl))
-                    last_sdf = dl;
-                last_lazy = false;
-            }
-            // findIntersectionBisection (:166-187)
-            float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
-            float cx = 0.0f, cy = 0.0f, cz = 0.0f;
-            bool ok = true;
+
+#ifdef SPSG_STATS
+                const long long clk1 = clock64();
+#endif
+                if (!maps_ready) {  // the chunk's maps have landed in shared memory
+                    mbar_wait(mbar, phase);
+                    maps_ready = true;
+                }
+#ifdef SPSG_STATS
+                const long long clk1b = clock64();
+#endif
+
+                // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the
+                // sign the cell class guarantees; the value is computed if and when a crossing needs it.
+                float last_sdf = 0.0f, last_alpha = 0.0f;
+                bool last_ok = false, last_lazy = false;
+                float dist = 0.0f;
+                enum { kMarch = 0, kCross = 1, kDone = 2 };
+                int state = kMarch;
+
+                for (;;) {
+#ifdef SPSG_STATS
+                    const long long clk_a = clock64();
+#endif
+                    // ---- march.  The loop is warp-synchronous: all lanes take part in every vote and every iteration
+                    // handles one event per marching lane, so diverged lanes re-join at the bottom of each iteration
+                    // instead of running their iterations one group after the other.  An event is either a jump over
+                    // samples whose outcome is known from the block map, or one sample.
+                    while (__any_sync(kFull, state == kMarch)) {
+#ifdef SPSG_STATS
+                        my_iters++;
+#endif
+                        if (state == kMarch) {
+                            if (!(ray < t_end)) {  // kernel.cu:200
+                                state = kDone;
+                            } else {
+                                enum { kActExact = 0, kActDense = 1, kActInvalid = 2, kActSign = 3, kActJumpEmpty = 4, kActJumpSame = 5 };
+                                int act = kActExact, nadv = 1;
+                                float sgn = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f;
+                                const float px = __fmaf_rn(r.dx, ray, r.camx), py = __fmaf_rn(r.dy, ray, r.camy),
+                                            pz = __fmaf_rn(r.dz, ray, r.camz);
+                                const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+                                const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
+                                if (skip_ok && (unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
+                                    (unsigned)iz < (unsigned)a.dimz) {
+                                    // block map and cell class are fetched together (independent shared-memory addresses)
+                                    const int b = bmap[((iz >> kFineLog2) * a.nby + (iy >> kFineLog2)) * a.nbx + (ix >> kFineLog2)];
+                                    const uint2 word = vbits[(iz * a.dimy + iy) * a.wpr + (ix >> 5)];
+                                    wx = __fadd_rn(px, -fx); wy = __fadd_rn(py, -fy); wz = __fadd_rn(pz, -fz);
+                                    const float wlo = fminf(wx, fminf(wy, wz)), whi = fmaxf(wx, fmaxf(wy, wz));
+                                    if (b != 0 && wlo >= kBoxEps && whi <= 1.0f - kBoxEps) {
+                                        // p is inside an aligned uniform region of edge `size`, at least kBoxEps away from
+                                        // every cell face and hence from the region's faces: corner (0,0,0) of this sample
+                                        // and of every later one up to the region's (shrunk) exit lies in the region.
+                                        const int kind = b >> 3, size = 2 << (b & 7), mask = ~(size - 1);
+                                        // a sign-uniform region cannot be jumped while the last valid sample has the
+                                        // other sign: its first valid sample would be a crossing
+                                        const bool opposite = last_ok && ((kind == kKindPos && last_sdf < 0.0f) ||
+                                                                          (kind == kKindNeg && last_sdf > 0.0f));
+                                        if (!opposite) {
+                                            // exit face per axis = origin + (dir > 0 ? size : 0), shrunk by kBoxEps (folded
+                                            // into kx/ky/kz together with the camera position)
+                                            const float tx_ = __fmaf_rn((float)((ix & mask) + (size & sxm)), invx, kx);
+                                            const float ty_ = __fmaf_rn((float)((iy & mask) + (size & sym)), invy, ky);
+                                            const float tz_ = __fmaf_rn((float)((iz & mask) + (size & szm)), invz, kz);
+                                            const float tout = fminf(tx_, fminf(ty_, tz_));
+                                            // steps to the first sample beyond the region's exit
+                                            const int n = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, jump_cap));
+                                            if (kind == kKindEmpty) {
+                                                // every sample before that one is invalid (kernel.cu:131,259)
+                                                act = kActJumpEmpty; nadv = n;
+                                            } else if (n >= 2) {
+                                                // Samples up to the last one inside are invalid or share the region's sign,
+                                                // and so does the last valid one before them: no crossing.  Land on the
+                                                // last one inside; it is classified by its own cell and leaves the march
+                                                // state exactly as the reference's sample-by-sample walk would.
+                                                act = kActJumpSame; nadv = n - 1;
+                                            }
+                                        }
+                                    }
+                                    if (act == kActExact) {
+                                        // One sample, decided by its own cell.  With frac(p) clear of the cell faces the
+                                        // reference's corners are exactly floor(p) + {0,1}; the cell's class says whether
+                                        // all 8 are present and whether they share a sign.
+                                        const float g = frac_guard(v.guard, ix, iy, iz);
+                                        if (wlo >= g && whi <= 1.0f - g) {
+                                            const unsigned ca = (word.x >> (ix & 31)) & 1u, cb = (word.y >> (ix & 31)) & 1u;
+                                            if ((ca | cb) == 0u) {
+                                                act = kActInvalid;
+                                            } else {
+                                                act = kActDense;
+                                                if ((ca & cb) == 0u) {
+                                                    sgn = ca ? 1.0f : -1.0f;
+                                                    // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN)
+                                                    if (!(last_ok && __fmul_rn(last_sdf, sgn) < 0.0f)) act = kActSign;
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                                if (act <= kActDense) {
+                                    bool valid;
+                                    if (act == kActDense) {
+                                        dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
+                                        valid = dist == dist;
+                                    } else {
+                                        valid = sample_sdf(v, fast_ok, px, py, pz, dist);  // the reference's exact corner arithmetic
+                                    }
+                                    if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
+                                        state = kCross;
+                                    } else if (valid) {
+                                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                                    } else {
+                                        last_ok = false;  // :259
+                                    }
+                                } else if (act == kActSign) {
+                                    last_sdf = sgn; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
+                                } else if (act != kActJumpSame) {
+                                    last_ok = false;  // :259 (invalid sample, or a run of them)
+                                }
+                                if (state == kMarch) ray = (nadv == 1) ? __fadd_rn(ray, a.inc) : step.advance(ray, nadv);  // :257,:260
+                            }
+                        }
+                    }
+#ifdef SPSG_STATS
+                    const long long clk_b = clock64();
+                    clk_march += clk_b - clk_a;
+#endif
+                    // ---- refinement round: every lane is either waiting with a crossing or finished
+                    if (!__any_sync(kFull, state == kCross)) break;
+                    if (state == kCross) {
+                        if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
+                            float dl = last_sdf;
+                            if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
+                                           __fmaf_rn(r.dz, last_alpha, r.camz), dl))
+                                last_sdf = dl;
+                            last_lazy = false;
+                        }
+                        // findIntersectionBisection (:166-187)
+                        float ta = last_alpha, da = last_sdf, tb = ray, db = dist, c = 0.0f;
+                        float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+                        bool ok = true;
 #pragma unroll 1
-            for (int k = 0; k < 3; k++) {
-                c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
-                cx = __fmaf_rn(r.dx, c, r.camx);
-                cy = __fmaf_rn(r.dy, c, r.camy);
-                cz = __fmaf_rn(r.dz, c, r.camz);
-                float dc;
-                if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
-                    ok = false;
-                    break;
-                }
-                if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
-            }
-            if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
-                depth = __fdiv_rn(c, r.d2r);                                                     // :215
-                // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel
-                // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
-                // ever says otherwise the reference reads stale registers -- we keep marching instead.
-                const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
-                hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
-            }
-            if (hit >= 0) {
-                state = kDone;
-            } else {
-                last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
-                ray = __fadd_rn(ray, a.inc);                                           // :257
-                state = kMarch;
-            }
-        }
-    }
-
-    // ---- write-out (kernel.cu:276-285 init, :217-239 hit) through shared memory
-    const float ninf = __int_as_float(0xff800000);
-    const int tp = lane;  // pixel index inside the warp's 8x4 tile (row-major)
-    float *s_sem = s_sem_all + warp * 32 * 14, *s_col = s_col_all + warp * 32 * 3, *s_nrm = s_nrm_all + warp * 32 * 3,
-          *s_dep = s_dep_all + warp * 32;
-    float col0 = ninf, col1 = ninf, col2 = ninf, dep = ninf;
-    float sem[14];
-#pragma unroll
-    for (int k = 0; k < 14; k++) sem[k] = ninf;
-    float n0 = ninf, n1 = ninf, n2 = ninf;
-    bool first = false;
-    if (hit >= 0) {
-        const float *c = a.vals_color + (size_t)hit * 3, *n = a.vals_normal + (size_t)hit * 3;
-        col0 = __ldg(c + 0); col1 = __ldg(c + 1); col2 = __ldg(c + 2);
-        const float m0 = __ldg(n + 0), m1 = __ldg(n + 1), m2 = __ldg(n + 2);
-        if (!(m0 == 0.0f && m1 == 0.0f && m2 == 0.0f)) { n0 = m0; n1 = m1; n2 = m2; }  // :220
-        dep = depth;
-        const float2 *s2 = reinterpret_cast<const float2 *>(a.vals_semantic + (size_t)hit * 14);
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            const float2 t2 = __ldg(s2 + k);
-            sem[2 * k] = t2.x; sem[2 * k + 1] = t2.y;
-        }
-        const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
-        const int offset = atomicAdd(a.mapping3dto2d_num + row, 1);                            // :244
-        if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;  // :245-247
-        first = offset == 0;
-    }
-    {
-        // the first pixel of a (voxel, view) pair appends the pair to the backward's work list (one atomic per warp)
-        const unsigned m = __ballot_sync(kFull, first);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
-            base = __shfl_sync(kFull, base, 0);
-            if (first) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(hit, img);
-        }
-    }
-    s_col[tp * 3 + 0] = col0; s_col[tp * 3 + 1] = col1; s_col[tp * 3 + 2] = col2;
-    s_nrm[tp * 3 + 0] = n0; s_nrm[tp * 3 + 1] = n1; s_nrm[tp * 3 + 2] = n2;
-    s_dep[tp] = dep;
-#pragma unroll
-    for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(s_sem + tp * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
-    if (a.hits && active) a.hits[gpix] = hit;
-
-    if (kLoss) {
-        float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (hit >= 0) {
-            const LossArgs &L = a.loss;
-            if (L.target_depth) {  // train.py:635-638
-                const float t = __ldg(L.target_depth + gpix);
-                if (t != 0.0f) { acc[0] = fabsf(__fmul_rn(depth, L.voxelsize) - t); acc[1] = 1.0f; }
-            }
-            if (L.target_color) {  // loss.py:246-257
-                const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
-                const float *t = L.target_color + gpix * 3;
-                acc[2] = fabsf(__fadd_rn(__fmul_rn(col0, w), -__fmul_rn(__ldg(t + 0), w))) +
-                         fabsf(__fadd_rn(__fmul_rn(col1, w), -__fmul_rn(__ldg(t + 1), w))) +
-                         fabsf(__fadd_rn(__fmul_rn(col2, w), -__fmul_rn(__ldg(t + 2), w)));
-                acc[3] = 3.0f;
-            }
-            if (L.target_label) {  // train.py:744-746
-                const int y = L.target_label[gpix];
-                if (y < 14 && sem[0] != ninf) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
-                    float m = sem[0];
-#pragma unroll
-                    for (int k = 1; k < 14; k++) m = fmaxf(m, sem[k]);
-                    float s = 0.0f, ly = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 14; k++) {
-                        s += expf(sem[k] - m);
-                        if (k == y) ly = sem[k];
+                        for (int k = 0; k < 3; k++) {
+                            c = __fmaf_rn(__fadd_rn(tb, -ta), __fdiv_rn(da, __fadd_rn(da, -db)), ta);  // :161
+                            cx = __fmaf_rn(r.dx, c, r.camx);
+                            cy = __fmaf_rn(r.dy, c, r.camy);
+                            cz = __fmaf_rn(r.dz, c, r.camz);
+                            float dc;
+                            if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
+                                ok = false;
+                                break;
+                            }
+                            if (__fmul_rn(da, dc) > 0.0f) { ta = c; da = dc; } else { tb = c; db = dc; }  // :180-181
+                        }
+                        if (ok && fabsf(__fadd_rn(last_sdf, -dist)) < a.thresh && fabsf(dist) < a.thresh) {  // :211-213
+                            depth = __fdiv_rn(c, r.d2r);                                                     // :215
+                            // payload voxel = nearest voxel of the last refinement point (:129) == hit voxel
+                            // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
+                            // ever says otherwise the reference reads stale registers -- we keep marching instead.
+                            const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
+                            hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
+                        }
+                        if (hit >= 0) {
+                            state = kDone;
+                        } else {
+                            last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
+                            ray = __fadd_rn(ray, a.inc);                                           // :257
+                            state = kMarch;
+                        }
                     }
-                    const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
-                    acc[4] = w * (logf(s) + m - ly);
-                    acc[5] = w;
+#ifdef SPSG_STATS
+                    clk_refine += clock64() - clk_b;
+#endif
                 }
+#ifdef SPSG_STATS
+                const long long clk2 = clock64();
+#endif
+
+                // ---- write-out (kernel.cu:276-285 init, :217-239 hit) through shared memory
+                const float ninf = __int_as_float(0xff800000);
+                float col0 = ninf, col1 = ninf, col2 = ninf, dep = ninf;
+                float sem[14];
+#pragma unroll
+                for (int k = 0; k < 14; k++) sem[k] = ninf;
+                float n0 = ninf, n1 = ninf, n2 = ninf;
+                bool first = false;
+                if (hit >= 0) {
+                    const float *c = a.vals_color + (size_t)hit * 3, *n = a.vals_normal + (size_t)hit * 3;
+                    col0 = __ldg(c + 0); col1 = __ldg(c + 1); col2 = __ldg(c + 2);
+                    const float m0 = __ldg(n + 0), m1 = __ldg(n + 1), m2 = __ldg(n + 2);
+                    if (!(m0 == 0.0f && m1 == 0.0f && m2 == 0.0f)) { n0 = m0; n1 = m1; n2 = m2; }  // :220
+                    dep = depth;
+                    const float2 *s2 = reinterpret_cast<const float2 *>(a.vals_semantic + (size_t)hit * 14);
+#pragma unroll
+                    for (int k = 0; k < 7; k++) {
+                        const float2 t2 = __ldg(s2 + k);
+                        sem[2 * k] = t2.x; sem[2 * k + 1] = t2.y;
+                    }
+                    const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
+                    const int offset = atomicAdd(a.mapping3dto2d_num + row, 1);                            // :244
+                    if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;  // :245-247
+                    first = offset == 0;
+                }
+                {
+                    // the first pixel of a (voxel, view) pair appends the pair to the backward's work list (one atomic
+                    // per warp)
+                    const unsigned m = __ballot_sync(kFull, first);
+                    if (m) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
+                        base = __shfl_sync(kFull, base, 0);
+                        if (first) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(hit, img);
+                    }
+                }
+                if (a.hits && active) a.hits[gpix] = hit;
+
+                if (kLoss) {
+                    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                    if (hit >= 0) {
+                        const LossArgs &L = a.loss;
+                        if (L.target_depth) {  // train.py:635-638
+                            const float t = __ldg(L.target_depth + gpix);
+                            if (t != 0.0f) { acc[0] = fabsf(__fmul_rn(depth, L.voxelsize) - t); acc[1] = 1.0f; }
+                        }
+                        if (L.target_color) {  // loss.py:246-257
+                            const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+                            const float *t = L.target_color + gpix * 3;
+                            acc[2] = fabsf(__fadd_rn(__fmul_rn(col0, w), -__fmul_rn(__ldg(t + 0), w))) +
+                                     fabsf(__fadd_rn(__fmul_rn(col1, w), -__fmul_rn(__ldg(t + 1), w))) +
+                                     fabsf(__fadd_rn(__fmul_rn(col2, w), -__fmul_rn(__ldg(t + 2), w)));
+                            acc[3] = 3.0f;
+                        }
+                        if (L.target_label) {  // train.py:744-746
+                            const int y = L.target_label[gpix];
+                            if (y < 14 && sem[0] != ninf) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+                                float m = sem[0];
+#pragma unroll
+                                for (int k = 1; k < 14; k++) m = fmaxf(m, sem[k]);
+                                float s = 0.0f, ly = 0.0f;
+#pragma unroll
+                                for (int k = 0; k < 14; k++) {
+                                    s += expf(sem[k] - m);
+                                    if (k == y) ly = sem[k];
+                                }
+                                const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+                                acc[4] = w * (logf(s) + m - ly);
+                                acc[5] = w;
+                            }
+                        }
+                    }
+                    float mine = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const float t = warp_sum(acc[k]);
+                        if (lane == k) mine = t;
+                    }
+                    // one double atomic per warp and term, spread over kLossSlots copies of the accumulators
+                    const unsigned slot = ((unsigned)tile * 7u + (unsigned)img * 11u) % kLossSlots;
+                    if (lane < 6 && mine != 0.0f) atomicAdd(a.loss.accum + slot * 8 + lane, (double)mine);
+                }
+                // the staging buffer is reused: semantic first, then colour + normal + depth
+                const bool vec = a.vec_ok != 0;
+#pragma unroll
+                for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(stage + lane * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
+                __syncwarp();
+                store_warp_tile<14>(stage, a.image_semantic, img, wx0, wy0, a.width, a.height, vec, lane);
+                __syncwarp();
+                float *s_col = stage, *s_nrm = stage + 96, *s_dep = stage + 192;
+                s_col[lane * 3 + 0] = col0; s_col[lane * 3 + 1] = col1; s_col[lane * 3 + 2] = col2;
+                s_nrm[lane * 3 + 0] = n0; s_nrm[lane * 3 + 1] = n1; s_nrm[lane * 3 + 2] = n2;
+                s_dep[lane] = dep;
+                __syncwarp();
+                store_warp_tile<3>(s_col, a.image_color, img, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<3>(s_nrm, a.image_normal, img, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<1>(s_dep, a.image_depth, img, wx0, wy0, a.width, a.height, vec, lane);
+                __syncwarp();
+#ifdef SPSG_STATS
+                if (lane == 0) {
+                    const long long clk3 = clock64();
+                    STAT_ADD(16, clk1 - clk0); STAT_MAX(17, clk1 - clk0);        // setup + clip
+                    STAT_ADD(28, clk1b - clk1); STAT_MAX(29, clk1b - clk1);      // wait for the maps
+                    STAT_ADD(18, clk_march); STAT_MAX(19, clk_march);            // march
+                    STAT_ADD(20, clk_refine); STAT_MAX(21, clk_refine);          // refinement
+                    STAT_ADD(22, clk3 - clk2); STAT_MAX(23, clk3 - clk2);        // epilogue
+                    STAT_ADD(24, clk3 - clk0); STAT_MAX(25, clk3 - clk0);        // whole tile
+                    STAT_MAX(26, my_iters);
+                    STAT_ADD(27, my_iters);
+                    int bucket = 0;
+                    for (int t = my_iters; t > 8; t >>= 1) bucket++;
+                    STAT_ADD(32 + min(bucket, 9), 1);
+                }
+#endif
+            }
+            tile = __shfl_sync(kFull, next, 0);
+        }
+        if (a.maps_in_smem) {
+            // every thread consumes this phase (a CTA must not retire, or refill, with a bulk copy in flight)
+            if (!maps_ready) mbar_wait(mbar, phase);
+            phase ^= 1u;
+            if (chunk + (int)gridDim.x < a.num_chunks) {
+                __syncthreads();  // all warps are done reading the maps before the next chunk's copy overwrites them
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
         }
-        float mine = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const float t = warp_sum(acc[k]);
-            if (lane == k) mine = t;
-        }
-        // one double atomic per warp and term, spread over kLossSlots copies of the accumulators
-        const unsigned slot = (blockIdx.x * 4u + blockIdx.y * 37u + blockIdx.z * 11u + warp) % kLossSlots;
-        if (lane < 6 && mine != 0.0f) atomicAdd(a.loss.accum + slot * 8 + lane, (double)mine);
     }
-    __syncwarp();
-    const bool vec = a.vec_ok != 0;
-    const int wx0 = x0 + (warp & 1) * kWarpW, wy0 = y0 + (warp >> 1) * kWarpH;
-    store_warp_tile<14>(s_sem, a.image_semantic, img, wx0, wy0, a.width, a.height, vec, lane);
-    store_warp_tile<3>(s_col, a.image_color, img, wx0, wy0, a.width, a.height, vec, lane);
-    store_warp_tile<3>(s_nrm, a.image_normal, img, wx0, wy0, a.width, a.height, vec, lane);
-    store_warp_tile<1>(s_dep, a.image_depth, img, wx0, wy0, a.width, a.height, vec, lane);
 }
-
 
 
 // loss_out[0..3] = depth, colour, semantic, weighted total; [4..6] = normalisers the backward needs.
@@ -966,16 +1126,15 @@ __device__ __forceinline__ void zero_rows(const BackwardArgs &a, long long first
     }
 }
 
-__global__ void __launch_bounds__(128) backward_zero_kernel(const BackwardArgs a) {
+__global__ void __launch_bounds__(256) backward_zero_kernel(const BackwardArgs a) {
     zero_rows<false>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
-// Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal),
-// accumulated as acc += g * inv (kernel.cu:398-418: val = grad / count, then add).  Plain variant: read from the four
-// gradient images.  Fused variant: recomputed from the rendering and the targets of the 2D losses.
+// Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal).
+// Plain variant: read from the four gradient images.  Fused variant: recomputed from the rendering and the targets
+// of the 2D losses.
 template <bool kFused>
-__device__ __forceinline__ void accumulate_pixel(const BackwardArgs &a, unsigned gpix, float inv, float (&acc)[21]) {
-    float g[21];
+__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix, float (&g)[21]) {
     if (!kFused) {
         const float2 *s2 = reinterpret_cast<const float2 *>(a.grad_semantic + (size_t)gpix * 14);
 #pragma unroll
@@ -1035,68 +1194,64 @@ __device__ __forceinline__ void accumulate_pixel(const BackwardArgs &a, unsigned
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 21; k++) acc[k] = __fmaf_rn(g[k], inv, acc[k]);
 }
 
 // The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
-// thread per item: pair -> pixel count and first four registered pixel ids (one round trip) -> the pixels' 21 upstream
-// gradients (independent 8-byte / 4-byte loads), accumulated as grad / count in registration order -- a fixed order,
-// so with one view per chunk the result is deterministic and written with plain stores.  With several views per chunk
-// the per-view means of a voxel are summed with float atomics onto rows the zero kernel cleared (kAtomic).
+// warp per item.  Lane k fetches the k-th registered pixel id (one coalesced load) and that pixel's 21 upstream
+// gradients (independent 8- and 4-byte loads), parks them in shared memory, and lane c then adds column c in
+// registration order as grad / count (kernel.cu:398-418) -- a fixed order, so with one view per chunk the result is
+// deterministic and written with plain stores.  With several views per chunk the per-view means of a voxel are summed
+// with float atomics onto rows the zero kernel cleared (kAtomic).
+constexpr int kGatherWarps = 8;
+
 template <bool kFused, bool kAtomic>
-__global__ void __launch_bounds__(128) backward_gather_kernel(const BackwardArgs a) {
+__global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(const BackwardArgs a) {
     if ((int)blockIdx.x < a.zero_blocks) {
         zero_rows<true>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)a.zero_blocks * blockDim.x);
         return;
     }
-    const int stride = (int)(gridDim.x - a.zero_blocks) * blockDim.x;
+    __shared__ float s_g[kGatherWarps][32 * 21];
+    const unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *tile = s_g[warp];
+    const int warps_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps;
     const int count = *a.list_count;
     const unsigned P = (unsigned)(a.width * a.height);
-    for (int item = ((int)blockIdx.x - a.zero_blocks) * blockDim.x + threadIdx.x; item < count; item += stride) {
-        const int2 e = a.list[item];
+    int item = ((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp;
+    int2 e = item < count ? a.list[item] : make_int2(0, 0);
+    while (item < count) {
         const int idx = e.x, img = e.y;
+        const int next_item = item + warps_total;
+        if (next_item < count) e = a.list[next_item];  // prefetch the next pair
         const size_t row = (size_t)(img % a.views) * a.num_locs + idx;
         const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
-        // both loads depend only on the pair: one round trip
-        int cnt = __ldg(a.mapping3dto2d_num + row);
-        int4 p4 = make_int4(0, 0, 0, 0);
-        if (a.vec4_ok) {
-            p4 = __ldg(reinterpret_cast<const int4 *>(prow));
-        } else {
-            p4.x = __ldg(prow);
-            if (a.max_pixels > 1) p4.y = __ldg(prow + 1);
-            if (a.max_pixels > 2) p4.z = __ldg(prow + 2);
-            if (a.max_pixels > 3) p4.w = __ldg(prow + 3);
-        }
-        cnt = min(max(cnt, 0), a.max_pixels);  // kernel.cu:392-393
+        const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
         const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
         const float inv = __frcp_rn((float)max(cnt, 1));
-        float acc[21];
+        float acc = 0.0f;
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int m = min(32, cnt - k0);
+            if (lane < m) {
+                float g[21];
+                pixel_grads<kFused>(a, pixbase + (unsigned)__ldg(prow + k0 + lane), g);
 #pragma unroll
-        for (int k = 0; k < 21; k++) acc[k] = 0.0f;
-        if (cnt > 0) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.x, inv, acc);
-        if (cnt > 1) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.y, inv, acc);
-        if (cnt > 2) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.z, inv, acc);
-        if (cnt > 3) accumulate_pixel<kFused>(a, pixbase + (unsigned)p4.w, inv, acc);
-#pragma unroll 1
-        for (int k = 4; k < cnt; k++) accumulate_pixel<kFused>(a, pixbase + (unsigned)__ldg(prow + k), inv, acc);
-        float *ds = a.d_semantic + (size_t)idx * 14, *dc = a.d_color + (size_t)idx * 3, *dn = a.d_normal + (size_t)idx * 3;
-        if (kAtomic) {
-#pragma unroll
-            for (int k = 0; k < 14; k++) atomicAdd(ds + k, acc[k]);
-#pragma unroll
-            for (int k = 0; k < 3; k++) atomicAdd(dc + k, acc[14 + k]);
-            atomicAdd(a.d_depth + idx, acc[17]);
-#pragma unroll
-            for (int k = 0; k < 3; k++) atomicAdd(dn + k, acc[18 + k]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(ds)[k] = make_float2(acc[2 * k], acc[2 * k + 1]);
-            dc[0] = acc[14]; dc[1] = acc[15]; dc[2] = acc[16];
-            a.d_depth[idx] = acc[17];
-            dn[0] = acc[18]; dn[1] = acc[19]; dn[2] = acc[20];
+                for (int c = 0; c < 21; c++) tile[lane * 21 + c] = g[c];
+            }
+            __syncwarp();
+            if (lane < 21)
+                for (int r = 0; r < m; r++) acc = __fmaf_rn(tile[r * 21 + lane], inv, acc);
+            __syncwarp();
         }
+        float *dst = nullptr;
+        if (lane < 14) dst = a.d_semantic + (size_t)idx * 14 + lane;
+        else if (lane < 17) dst = a.d_color + (size_t)idx * 3 + (lane - 14);
+        else if (lane == 17) dst = a.d_depth + idx;
+        else if (lane < 21) dst = a.d_normal + (size_t)idx * 3 + (lane - 18);
+        if (dst) {
+            if (kAtomic) atomicAdd(dst, acc);
+            else *dst = acc;
+        }
+        item = next_item;
     }
 }
 
@@ -1239,7 +1394,8 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     if (reinterpret_cast<uintptr_t>(workspace) & 255u) return fail(SPSG_ERR_INVALID_ARGUMENT, "workspace must be 256-byte aligned");
     uint8_t *ws = (uint8_t *)workspace;
     float *dense = (float *)(ws + L.dense_off);
-    uint8_t *cmap = ws + L.cmap_off, *bmap = ws + L.bmap_off, *marks = ws + L.marks_off;
+    uint2 *vbits = (uint2 *)(ws + L.vbit_off);
+    uint8_t *bmap = ws + L.bmap_off, *marks = ws + L.marks_off;
     double *accum = (double *)(ws + L.loss_off);
     const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
     const int sms = sm_count();
@@ -1270,11 +1426,9 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     }
     const size_t plane_stride = (size_t)p->num_chunks * L.bpc;
     {
-        const int wpr = (p->dimx + 31) / 32;
-        const long long vwarps = (long long)p->num_chunks * p->dimz * p->dimy * wpr;
-        cell_class_kernel<<<(unsigned)((vwarps + 7) / 8), 256, 0, st>>>(dense, cmap, marks, plane_stride, p->num_chunks,
-                                                                       p->dimz, p->dimy, p->dimx, wpr, L.nbz, L.nby,
-                                                                       L.nbx, L.bpc);
+        const dim3 cgrid((unsigned)((p->dimy * L.wpr + 7) / 8), (unsigned)p->dimz, (unsigned)p->num_chunks);
+        cell_class_kernel<<<cgrid, 256, 0, st>>>(dense, vbits, L.vpc, marks, plane_stride, p->dimz, p->dimy, p->dimx, L.wpr,
+                                                 L.nby, L.nbx, L.bpc);
         CUDA_TRY(cudaGetLastError());
         const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
                   sbz = (L.nbz + kSuper - 1) / kSuper;
@@ -1290,8 +1444,11 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_color = image_color; a.image_depth = image_depth; a.image_normal = image_normal;
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
-    a.dense = dense; a.cmap = cmap; a.bmap = bmap; a.bpc = L.bpc;
-    a.bmap_in_smem = L.bpc <= (size_t)kMaxSmemBlockMap;
+    a.dense = dense; a.vbits = vbits; a.bmap = bmap; a.vpc = L.vpc; a.bpc = L.bpc; a.wpr = L.wpr;
+    const size_t map_bytes = L.vpc * sizeof(uint2) + L.bpc;
+    a.maps_in_smem = kFwdSmemFixed + map_bytes <= kFwdSmemMax;
+    a.tile_counter = (int32_t *)(ws + L.tiles_off);
+    a.num_chunks = p->num_chunks;
     a.list_count = (int32_t *)(ws + L.head_off);
     a.list = (int2 *)(ws + L.list_off);
     a.hits = (p->flags & SPSG_FLAG_RECORD_HITS) ? (int32_t *)(ws + L.hits_off) : nullptr;
@@ -1304,14 +1461,33 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.flags = p->flags;
     a.vec_ok = (p->width % 4 == 0) && aligned16(image_color) && aligned16(image_depth) && aligned16(image_normal) &&
                aligned16(image_semantic);
+    {
+        int k = 0;
+        while ((1 << k) < std::max(p->dimx, std::max(p->dimy, p->dimz))) k++;
+        a.guard = std::min(kFracGuard, std::max(ldexpf(1.0f, k - 21), ldexpf(1.0f, -18)));  // 8 ulp of the largest coordinate
+    }
     a.loss = make_loss_args(targets, accum);
-    const dim3 grid((p->width + kTileW - 1) / kTileW, (p->height + kTileH - 1) / kTileH,
-                    p->num_chunks * p->views_per_chunk);
-    const size_t dyn = a.bmap_in_smem ? L.bpc : 0;
+    // persistent: one CTA per SM (fewer when there is less than one tile per warp)
+    const long long tiles_x = (p->width + kWarpW - 1) / kWarpW, tiles_y = (p->height + kWarpH - 1) / kWarpH;
+    const long long all_tiles = ((tiles_x + 1) / 2) * ((tiles_y + 1) / 2) * 4 * p->views_per_chunk * p->num_chunks;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(sms, (all_tiles + kFwdWarps - 1) / kFwdWarps));
+    const size_t dyn = kFwdSmemFixed + (a.maps_in_smem ? map_bytes : 0);
+    {
+        static std::mutex mu;
+        static bool configured[64] = {false};
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+    }
     if (targets) {
         {
             ScopedKernelTimer timer(0, st);
-            raycast_forward_kernel<true><<<grid, kTilePix, dyn, st>>>(a);
+            raycast_forward_kernel<true><<<grid, kFwdThreads, dyn, st>>>(a);
         }
         CUDA_TRY(cudaGetLastError());
         finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
@@ -1319,7 +1495,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
                                               targets->target_color != nullptr, targets->target_label != nullptr);
     } else {
         ScopedKernelTimer timer(0, st);
-        raycast_forward_kernel<false><<<grid, kTilePix, dyn, st>>>(a);
+        raycast_forward_kernel<false><<<grid, kFwdThreads, dyn, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
@@ -1363,23 +1539,23 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     a.num_locs = p->num_locs;
     a.vec4_ok = (p->max_pixels_per_voxel % 4 == 0) && aligned16(mapping3dto2d);
     const int sms = sm_count();
-    // one thread per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
+    // one warp per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
     const long long max_items = p->num_locs * p->views_per_chunk;
-    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + 127) / 128, (long long)sms * 16));
-    const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 127) / 128, (long long)sms * 8);
+    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + kGatherWarps - 1) / kGatherWarps, (long long)sms * 8));
+    const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 255) / 256, (long long)sms * 4);
     if (p->views_per_chunk == 1) {
         // one launch: leading CTAs clear the rows of voxels nothing hit, the rest gather (plain stores)
         a.zero_blocks = (int)zero_blocks;
         ScopedKernelTimer timer(1, st);
-        if (fused) backward_gather_kernel<true, false><<<zero_blocks + gather_blocks, 128, 0, st>>>(a);
-        else backward_gather_kernel<false, false><<<zero_blocks + gather_blocks, 128, 0, st>>>(a);
+        if (fused) backward_gather_kernel<true, false><<<zero_blocks + gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        else backward_gather_kernel<false, false><<<zero_blocks + gather_blocks, kGatherWarps * 32, 0, st>>>(a);
     } else {
         a.zero_blocks = 0;
-        backward_zero_kernel<<<zero_blocks, 128, 0, st>>>(a);
+        backward_zero_kernel<<<zero_blocks, 256, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         ScopedKernelTimer timer(1, st);
-        if (fused) backward_gather_kernel<true, true><<<gather_blocks, 128, 0, st>>>(a);
-        else backward_gather_kernel<false, true><<<gather_blocks, 128, 0, st>>>(a);
+        if (fused) backward_gather_kernel<true, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        else backward_gather_kernel<false, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
@@ -1388,6 +1564,17 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
 }  // namespace
 
 extern "C" {
+
+#ifdef SPSG_STATS
+SPSG_API int spsg_debug_stats(unsigned long long *out, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_stats, sizeof(unsigned long long) * 48) != cudaSuccess) return SPSG_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[48] = {0};
+        cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+    }
+    return SPSG_OK;
+}
+#endif
 
 const char *spsg_version(void) { return "spsg_raycast_b200 0.3 (sm_100a)"; }
 const char *spsg_last_error(void) { return g_err; }
