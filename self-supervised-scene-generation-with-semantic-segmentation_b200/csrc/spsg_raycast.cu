@@ -209,42 +209,49 @@ __device__ __forceinline__ Ray setup_ray(const float *__restrict__ M, const floa
 // as every partial sum stays below 2^(e+1) - inc.  Anything irregular falls back to real adds.
 struct Stepper {
     float inc, inv_inc;
-    float lo, lim, d, inv_d;  // current binade [lo, 2lo); closed form usable while ray < lim
+    float lo, hi, lim, d, inv_d;  // current binade [lo, hi = 2lo); closed form usable while ray < lim
     bool regular;
 
     __device__ __forceinline__ void init(float inc_) {
         inc = inc_;
         inv_inc = rcp_approx(inc_);
-        lo = 0.0f; lim = 0.0f; d = inc_; inv_d = inv_inc; regular = false;
+        lo = 0.0f; hi = 0.0f; lim = 0.0f; d = inc_; inv_d = inv_inc; regular = false;
     }
     __device__ __forceinline__ void rebin(float ray) {
         lo = __uint_as_float(__float_as_uint(ray) & 0x7f800000u);      // 2^e <= ray
+        hi = __fmul_rn(lo, 2.0f);
         const float u = __fmul_rn(lo, 1.1920928955078125e-07f);         // 2^(e-23)
         d = __fadd_rn(__fadd_rn(lo, inc), -lo);                         // inc on the u grid
         const float rem = __fadd_rn(inc, -d);                           // exact remainder
         regular = (lo >= 1.0f) && (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) && (d > 0.0f) &&
                   (__fmul_rn(fabsf(rem), 2.0f) != u);
-        lim = __fadd_rn(__fmul_rn(lo, 2.0f), -__fmul_rn(inc, 2.0f));   // partial sums must stay below 2lo - inc
+        lim = __fadd_rn(hi, -__fmul_rn(inc, 2.0f));                    // partial sums must stay below 2lo - inc
         inv_d = rcp_approx(d);
     }
-    // advance by `want` >= 1 steps, or by fewer (>= 1) when the closed form would leave the binade
-    __device__ __forceinline__ float advance(float ray, int want) {
-        if (want <= 2) {
-            ray = __fadd_rn(ray, inc);
-            if (want == 2) ray = __fadd_rn(ray, inc);
-            return ray;
+    // exactly n >= 1 steps of `ray = ray + inc`
+    __device__ __forceinline__ float advance(float ray, int n) {
+        for (;;) {
+            if (n <= 2) {
+                ray = __fadd_rn(ray, inc);
+                if (n == 2) ray = __fadd_rn(ray, inc);
+                return ray;
+            }
+            if (!(ray >= lo && ray < hi)) rebin(ray);
+            int j = 0;
+            if (regular) {
+                // floor((lim - ray)/d) computed approximately; the slack inc + d in `lim` dwarfs the error
+                const float room = lim - ray;
+                j = (room > 0.0f) ? min(n, __float2int_rd(room * inv_d)) : 0;
+            }
+            if (j >= 1) {
+                ray = __fmaf_rn((float)j, d, ray);
+                n -= j;
+                if (n == 0) return ray;
+            } else {  // top of the binade (the add that crosses it rounds on the next grid), or an irregular binade
+                ray = __fadd_rn(ray, inc);
+                n -= 1;
+            }
         }
-        if (!(ray >= lo && ray < __fmul_rn(lo, 2.0f))) rebin(ray);
-        if (regular) {
-            const float room = lim - ray;
-            // floor((lim - ray)/d) computed approximately; the slack inc + d in `lim` dwarfs the error
-            const int jmax = (room > 0.0f) ? __float2int_rd(room * inv_d) : 0;
-            const int j = min(want, jmax);
-            if (j >= 1) return __fmaf_rn((float)j, d, ray);
-            return __fadd_rn(ray, inc);
-        }
-        for (int k = 0; k < want; k++) ray = __fadd_rn(ray, inc);
-        return ray;
     }
 };
 
