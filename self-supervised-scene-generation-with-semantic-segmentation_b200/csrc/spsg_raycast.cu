@@ -97,8 +97,8 @@ struct Layout {
     size_t vbit_off, vbit_bytes;    // uint2 [B][vpc]: bit x of (.x, .y) = class of the sample cell whose corner (0,0,0)
                                     // is the voxel: 00 invalid, 10 positive, 01 negative, 11 mixed
     size_t bmap_off, bmap_bytes;    // u8  [B][bpc] block map
-    size_t zero_off, zero_bytes;    // everything below is cleared by the fill kernel of every forward
     size_t marks_off, marks_bytes;  // u8  [3][B][bpc]: block holds a positive / negative / mixed cell
+    size_t zero_off, zero_bytes;    // everything from here to the list is cleared by the fill kernel of every forward
     size_t head_off;                // int32 list counter (256 B)
     size_t tiles_off, tiles_bytes;  // int32 [B] dynamic tile counters of the forward
     size_t loss_off, loss_bytes;    // double[kLossSlots][8] loss accumulators
@@ -127,10 +127,10 @@ Layout make_layout(const spsg_raycast_params *p) {
     L.bmap_off = off;
     L.bmap_bytes = align_up((size_t)p->num_chunks * L.bpc, 256);
     off += L.bmap_bytes;
-    L.zero_off = off;
     L.marks_off = off;
     L.marks_bytes = align_up((size_t)3 * p->num_chunks * L.bpc, 256);
     off += L.marks_bytes;
+    L.zero_off = off;
     L.head_off = off;
     off += 256;
     L.tiles_off = off;
@@ -254,6 +254,49 @@ struct Stepper {
         }
     }
 };
+
+// The same recurrence with the per-binade constants (they depend on inc only) tabulated once per CTA in shared
+// memory: entry e describes the binade [2^e, 2^(e+1)) as (d, 1/d, lim, -); lim = -inf marks a binade where the closed
+// form is not usable (entry 32 serves every ray parameter outside [1, 2^32)).
+constexpr int kStepEntries = 33;
+
+__device__ __forceinline__ void step_table_fill(float4 *table, int e, float inc) {
+    float4 t = make_float4(inc, 0.0f, -CUDART_INF_F, 0.0f);
+    if (e < 32) {
+        const float lo = __uint_as_float((unsigned)(e + 127) << 23), hi = __fmul_rn(lo, 2.0f);
+        const float u = __fmul_rn(lo, 1.1920928955078125e-07f);  // 2^(e-23)
+        const float d = __fadd_rn(__fadd_rn(lo, inc), -lo);       // inc on the u grid
+        const float rem = __fadd_rn(inc, -d);                     // exact remainder
+        const bool regular = (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) && (d > 0.0f) &&
+                             (__fmul_rn(fabsf(rem), 2.0f) != u);
+        if (regular) t = make_float4(d, rcp_approx(d), __fadd_rn(hi, -__fmul_rn(inc, 2.0f)), 0.0f);
+    }
+    table[e] = t;
+}
+
+// exactly n >= 1 steps of `ray = ray + inc` (ray >= 0)
+__device__ __forceinline__ float step_advance(const float4 *table, float inc, float ray, int n) {
+    for (;;) {
+        if (n <= 2) {
+            ray = __fadd_rn(ray, inc);
+            if (n == 2) ray = __fadd_rn(ray, inc);
+            return ray;
+        }
+        const unsigned e = (__float_as_uint(ray) >> 23) - 127u;
+        const float4 t = table[min(e, 32u)];
+        // floor((lim - ray)/d) computed approximately; the slack inc + d in `lim` dwarfs the error
+        const float room = t.z - ray;
+        const int j = (room > 0.0f) ? min(n, __float2int_rd(room * t.y)) : 0;
+        if (j >= 1) {
+            ray = __fmaf_rn((float)j, t.x, ray);
+            n -= j;
+            if (n == 0) return ray;
+        }
+        // one real add: the next step of an irregular binade, or the one that crosses the top of this binade
+        ray = __fadd_rn(ray, inc);
+        if (--n == 0) return ray;
+    }
+}
 
 struct Volume {
     const int32_t *__restrict__ index;  // this chunk's slice of sparse_mapping
@@ -397,63 +440,73 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
 //            >= 0, they sum to ~1 so one is >= 1/8, and products with values above kTiny cannot underflow;
 //   negative likewise with all corners in (-kHuge, -kTiny): value < 0;
 //   mixed    all present, anything else: the value has to be computed.
-// Two bit planes per 32 cells of an x row (see Layout); one warp per word.  Also marks, per 4^3 block, whether it
-// holds a positive, a negative or a mixed cell (three byte planes, plain stores of 1: a benign race).
-// grid = (ceil(Dy*wpr / 8), Dz, B), block = 256.
+// Two bit planes per 32 cells of an x row (see Layout).  One warp per (4 y) x (4 z) x (32 x) slab, i.e. per run of
+// eight 4^3 blocks: it reads the 5 x 5 voxel rows once (all loads in flight together), emits the 16 class words and
+// -- being the only writer of those blocks -- their three marks (block holds a positive / negative / mixed cell).
+// grid = (ceil(nby*wpr / 4), nbz, B), block = 128.
 constexpr float kTiny = 1e-30f, kHuge = 3e38f;
 
-__global__ void __launch_bounds__(256) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
+__global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
                                                          size_t vpc, uint8_t *__restrict__ marks, size_t plane_stride,
                                                          int dimz, int dimy, int dimx, int wpr, int nby, int nbx,
                                                          size_t bpc) {
+    const unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);  // (y, xw) of this warp's word
-    if (w >= dimy * wpr) return;
-    const int y = w / wpr, xw = w - y * wpr;
-    const int z = blockIdx.y, chunk = blockIdx.z;
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);  // (block row in y, xw) of this warp's slab
+    if (w >= nby * wpr) return;
+    const int yb = w / wpr, xw = w - yb * wpr;
+    const int zb = blockIdx.y, chunk = blockIdx.z;
+    const int y0 = yb * kFine, z0 = zb * kFine;
     const float *__restrict__ base = dense + (size_t)chunk * dimz * dimy * dimx;
-    const bool inner = (y + 1 < dimy) && (z + 1 < dimz);  // warp-uniform
-    // per x column (x, y..y+1, z..z+1): all present / all positive class / all negative class
-    bool col = false, pos = false, neg = false, coln = false, posn = false, negn = false;
-    if (inner) {
-        const size_t o00 = ((size_t)z * dimy + y) * dimx, o10 = o00 + dimx, o01 = o00 + (size_t)dimy * dimx,
-                     o11 = o01 + dimx;
-        const int x = xw * 32 + lane;
-        if (x < dimx) {
-            const float a = __ldg(base + o00 + x), b = __ldg(base + o10 + x), c = __ldg(base + o01 + x),
-                        d = __ldg(base + o11 + x);
-            col = (a == a) && (b == b) && (c == c) && (d == d);
-            const float lo = fminf(fminf(a, b), fminf(c, d)), hi = fmaxf(fmaxf(a, b), fmaxf(c, d));
-            pos = col && lo > kTiny && hi < kHuge;
-            neg = col && hi < -kTiny && lo > -kHuge;
+    const int x = xw * 32 + lane, xn = xw * 32 + 32;
+    // voxel rows (y0..y0+4, z0..z0+4): value of this lane's voxel, and of the first voxel of the next word for lane 0
+    float val[5][5], nxt[5][5];
+#pragma unroll
+    for (int dz = 0; dz < 5; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 5; dy++) {
+            const int y = y0 + dy, z = z0 + dz;
+            const bool row = y < dimy && z < dimz;
+            const size_t o = ((size_t)z * dimy + y) * dimx;
+            val[dz][dy] = (row && x < dimx) ? __ldg(base + o + x) : CUDART_NAN_F;
+            nxt[dz][dy] = (row && lane == 0 && xn < dimx) ? __ldg(base + o + xn) : CUDART_NAN_F;
         }
-        const int xn = xw * 32 + 32;
-        if (lane == 0 && xn < dimx) {
-            const float a = __ldg(base + o00 + xn), b = __ldg(base + o10 + xn), c = __ldg(base + o01 + xn),
-                        d = __ldg(base + o11 + xn);
-            coln = (a == a) && (b == b) && (c == c) && (d == d);
-            const float lo = fminf(fminf(a, b), fminf(c, d)), hi = fmaxf(fmaxf(a, b), fmaxf(c, d));
-            posn = coln && lo > kTiny && hi < kHuge;
-            negn = coln && hi < -kTiny && lo > -kHuge;
+    // per voxel row: present / positive-class / negative-class masks over x, shifted so that bit x also covers x+1
+    unsigned pres[5][5], posm[5][5], negm[5][5];
+#pragma unroll
+    for (int dz = 0; dz < 5; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 5; dy++) {
+            const float a = val[dz][dy], n = nxt[dz][dy];
+            const unsigned p = __ballot_sync(kFull, a == a), pp = __ballot_sync(kFull, a > kTiny && a < kHuge),
+                           pn = __ballot_sync(kFull, a < -kTiny && a > -kHuge);
+            // lane 0 holds the next word's first voxel
+            const unsigned np = __shfl_sync(kFull, (unsigned)(n == n), 0), npp = __shfl_sync(kFull, (unsigned)(n > kTiny && n < kHuge), 0),
+                           npn = __shfl_sync(kFull, (unsigned)(n < -kTiny && n > -kHuge), 0);
+            pres[dz][dy] = p & ((p >> 1) | (np << 31));
+            posm[dz][dy] = pp & ((pp >> 1) | (npp << 31));
+            negm[dz][dy] = pn & ((pn >> 1) | (npn << 31));
         }
-    }
-#define SPSG_PAIR(m, mn) ((m) & (((m) >> 1) | (((mn) & 1u) << 31)))
-    const unsigned cb = __ballot_sync(0xffffffffu, col), cbn = __ballot_sync(0xffffffffu, coln);
-    const unsigned pb = __ballot_sync(0xffffffffu, pos), pbn = __ballot_sync(0xffffffffu, posn);
-    const unsigned nb = __ballot_sync(0xffffffffu, neg), nbn = __ballot_sync(0xffffffffu, negn);
-    const unsigned v = SPSG_PAIR(cb, cbn), vp = SPSG_PAIR(pb, pbn), vn = SPSG_PAIR(nb, nbn);
-#undef SPSG_PAIR
-    const unsigned vm = v & ~vp & ~vn;
-    if (lane == 0) vbits[(size_t)chunk * vpc + ((size_t)z * dimy + y) * wpr + xw] = make_uint2(v & ~vn, v & ~vp);
-    if (lane < 24) {  // lanes 0-7: positive plane, 8-15: negative, 16-23: mixed; 4 cells of one block per lane
+    unsigned any_pos = 0u, any_neg = 0u, any_mix = 0u;
+#pragma unroll
+    for (int dz = 0; dz < 4; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+            const int y = y0 + dy, z = z0 + dz;
+            const unsigned v = pres[dz][dy] & pres[dz][dy + 1] & pres[dz + 1][dy] & pres[dz + 1][dy + 1];
+            const unsigned vp = posm[dz][dy] & posm[dz][dy + 1] & posm[dz + 1][dy] & posm[dz + 1][dy + 1];
+            const unsigned vn = negm[dz][dy] & negm[dz][dy + 1] & negm[dz + 1][dy] & negm[dz + 1][dy + 1];
+            any_pos |= vp; any_neg |= vn; any_mix |= v & ~vp & ~vn;
+            if (lane == 0 && y < dimy && z < dimz)
+                vbits[(size_t)chunk * vpc + ((size_t)z * dimy + y) * wpr + xw] = make_uint2(v & ~vn, v & ~vp);
+        }
+    if (lane < 24) {  // lanes 0-7: positive plane, 8-15: negative, 16-23: mixed; one block per lane
         const int plane = lane >> 3, g = lane & 7;
-        const unsigned m = plane == 0 ? vp : plane == 1 ? vn : vm;
-        if ((m >> (4 * g)) & 0xfu) {
-            const int bx = xw * 8 + g;
-            uint8_t *t = marks + (size_t)plane * plane_stride + (size_t)chunk * bpc +
-                         ((size_t)(z >> kFineLog2) * nby + (y >> kFineLog2)) * nbx + bx;
-            if (*reinterpret_cast<volatile uint8_t *>(t) == 0) *t = 1;  // benign race: everybody writes 1
-        }
+        const unsigned m = plane == 0 ? any_pos : plane == 1 ? any_neg : any_mix;
+        const int bx = xw * 8 + g;
+        if (bx < nbx)
+            marks[(size_t)plane * plane_stride + (size_t)chunk * bpc + ((size_t)zb * nby + yb) * nbx + bx] =
+                ((m >> (4 * g)) & 0xfu) ? 1 : 0;
     }
 }
 
@@ -509,6 +562,75 @@ __global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restric
     }
 }
 
+// The same block map, built by a whole CTA straight into shared memory (forward prologue, when the chunk's maps are
+// shared-memory resident): region bits are OR-ed level by level, no atomics.  `bm` receives the map (nblocks bytes),
+// `tmp` needs n8 + n16 + n32 bytes.  Ends with a __syncthreads().
+__device__ __forceinline__ uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
+    const int r[5] = {0, r1, r2, r3, r4};
+    int lu = 0, le = 0;
+#pragma unroll
+    for (int l = 1; l <= 4; l++) {
+        if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
+        if (r[l] == 0) le = l;
+    }
+    if (lu == 0) return 0;
+    const int kind = (le == lu) ? kKindEmpty : (r[lu] & 1) ? kKindPos : kKindNeg;
+    return (uint8_t)((kind << 3) | lu);
+}
+
+__device__ __forceinline__ void decode3(int i, int nx, int ny, float inv_nx, float inv_ny, int &x, int &y, int &z) {
+    // i = (z * ny + y) * nx + x for i < 2^22: quotients via fp32 reciprocals (exact after the +0.5 nudge)
+    const int q = __float2int_rz(((float)i + 0.5f) * inv_nx);
+    x = i - q * nx;
+    z = __float2int_rz(((float)q + 0.5f) * inv_ny);
+    y = q - z * ny;
+}
+
+__device__ void build_block_map_cta(const uint8_t *__restrict__ marks, size_t plane_stride, uint8_t *__restrict__ bm,
+                                    uint8_t *__restrict__ tmp, int nbx, int nby, int nbz, size_t bpc) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int nblocks = nbx * nby * nbz;
+    const int ax = (nbx + 1) >> 1, ay = (nby + 1) >> 1, az = (nbz + 1) >> 1;  // 8^3 regions
+    const int cx = (ax + 1) >> 1, cy = (ay + 1) >> 1, cz = (az + 1) >> 1;  // 16^3
+    const int ex = (cx + 1) >> 1, ey = (cy + 1) >> 1, ez = (cz + 1) >> 1;  // 32^3
+    uint8_t *a8 = tmp, *a16 = a8 + ax * ay * az, *a32 = a16 + cx * cy * cz;
+    {
+        // region bits of the 4^3 blocks, four blocks per 32-bit word (marks are 0/1 bytes; bpc is a multiple of 16)
+        const uint32_t *m0 = reinterpret_cast<const uint32_t *>(marks), *m1 = reinterpret_cast<const uint32_t *>(marks + plane_stride),
+                       *m2 = reinterpret_cast<const uint32_t *>(marks + 2 * plane_stride);
+        uint32_t *bm32 = reinterpret_cast<uint32_t *>(bm);
+        for (int i = tid; i < (int)(bpc >> 2); i += T) bm32[i] = __ldg(m0 + i) | (__ldg(m1 + i) << 1) | (__ldg(m2 + i) << 2);
+    }
+    __syncthreads();
+    // each level: OR of the (up to) 2x2x2 children
+    auto reduce = [&](const uint8_t *src, int sx, int sy, int sz, uint8_t *dst, int dx, int dy, int dz) {
+        const float inv_dx = 1.0f / (float)dx, inv_dy = 1.0f / (float)dy;
+        for (int j = tid; j < dx * dy * dz; j += T) {
+            int x, y, z;
+            decode3(j, dx, dy, inv_dx, inv_dy, x, y, z);
+            int bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int xx = 2 * x + (k & 1), yy = 2 * y + ((k >> 1) & 1), zz = 2 * z + (k >> 2);
+                if (xx < sx && yy < sy && zz < sz) bits |= src[(zz * sy + yy) * sx + xx];
+            }
+            dst[j] = (uint8_t)bits;
+        }
+        __syncthreads();
+    };
+    reduce(bm, nbx, nby, nbz, a8, ax, ay, az);
+    reduce(a8, ax, ay, az, a16, cx, cy, cz);
+    reduce(a16, cx, cy, cz, a32, ex, ey, ez);
+    const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
+    for (int i = tid; i < nblocks; i += T) {
+        int x, y, z;
+        decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
+        bm[i] = block_map_byte(bm[i], a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)],
+                               a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)], a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)]);
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -545,6 +667,8 @@ struct ForwardArgs {
     const float *dense;
     const uint2 *vbits;   // [B][vpc]
     const uint8_t *bmap;  // [B][bpc]
+    const uint8_t *marks; // [3][B][bpc], plane stride below
+    size_t plane_stride;
     size_t vpc, bpc;
     int wpr;
     int maps_in_smem;
@@ -572,7 +696,7 @@ constexpr int kFwdWarps = 24;                           // warps of the persiste
 constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
 constexpr size_t kFwdSmemFixed = 128 + (size_t)kFwdWarps * kStageFloats * sizeof(float);
-constexpr size_t kFwdSmemMax = 232448;                  // 227 KB opt-in limit per CTA
+constexpr size_t kFwdSmemMax = 232448 - 1024;           // 227 KB opt-in limit per CTA, minus the static shared memory
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -635,22 +759,24 @@ __device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, flo
 // CTA i works on chunk i % B (then i % B + gridDim, ...): the chunk's cell-class bit planes and block map are pulled
 // into shared memory once by TMA bulk copies, so the march's "does this sample need arithmetic" lookups never leave
 // the SM; tiles of the chunk's images are dealt to warps first statically, then from a global counter.
-template <bool kLoss>
+template <bool kLoss, bool kSmemMaps>
 __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const ForwardArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float4 s_steps[kStepEntries];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *stage = reinterpret_cast<float *>(smem + 128) + warp * kStageFloats;
     uint2 *s_vbits = reinterpret_cast<uint2 *>(smem + kFwdSmemFixed);
     uint8_t *s_bmap = reinterpret_cast<uint8_t *>(s_vbits + a.vpc);
+    uint8_t *s_tmp = s_bmap + a.bpc;
     const unsigned kFull = 0xffffffffu;
     const float kInf = CUDART_INF_F;
 
-    if (a.maps_in_smem) {
-        if (threadIdx.x == 0) mbar_init(mbar, 1);
-        __syncthreads();
-    }
+    if (threadIdx.x < kStepEntries) step_table_fill(s_steps, threadIdx.x, a.inc);
+    if (kSmemMaps && threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
     unsigned phase = 0;
+    const float inv_inc = rcp_approx(a.inc);
 
     const size_t cells = (size_t)a.dimz * a.dimy * a.dimx;
     const bool clip = !(a.flags & SPSG_FLAG_NO_CLIP);
@@ -664,17 +790,20 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
     const int total_tiles = tiles_per_image * a.views;
 
     for (int chunk = blockIdx.x % a.num_chunks; chunk < a.num_chunks; chunk += gridDim.x) {
-        if (a.maps_in_smem && threadIdx.x == 0) {
-            const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2)), bm_bytes = (unsigned)a.bpc;
-            mbar_expect_tx(mbar, vb_bytes + bm_bytes);
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(a.vbits + (size_t)chunk * a.vpc);
-            uint8_t *dst = reinterpret_cast<uint8_t *>(s_vbits);
-            for (unsigned o = 0; o < vb_bytes; o += 32768u) bulk_copy_g2s(dst + o, src + o, min(32768u, vb_bytes - o), mbar);
-            bulk_copy_g2s(s_bmap, a.bmap + (size_t)chunk * a.bpc, bm_bytes, mbar);
+        if (kSmemMaps) {
+            if (threadIdx.x == 0) {  // cell classes: TMA bulk copies, completion on the mbarrier
+                const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2));
+                mbar_expect_tx(mbar, vb_bytes);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.vbits + (size_t)chunk * a.vpc);
+                uint8_t *dst = reinterpret_cast<uint8_t *>(s_vbits);
+                for (unsigned o = 0; o < vb_bytes; o += 32768u) bulk_copy_g2s(dst + o, src + o, min(32768u, vb_bytes - o), mbar);
+            }
+            // block map: built here from the classifier's marks while the copy is in flight
+            build_block_map_cta(a.marks + (size_t)chunk * a.bpc, a.plane_stride, s_bmap, s_tmp, a.nbx, a.nby, a.nbz, a.bpc);
         }
-        bool maps_ready = !a.maps_in_smem;
-        const uint2 *vbits = a.maps_in_smem ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
-        const uint8_t *bmap = a.maps_in_smem ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
+        bool maps_ready = !kSmemMaps;
+        const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
+        const uint8_t *bmap = kSmemMaps ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
         Volume v;
         v.index = a.sparse_mapping + (size_t)chunk * cells;
         v.sdf = a.vals_sdf;
@@ -730,9 +859,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                 const float ky = r.dy != 0.0f ? ((r.dy > 0.0f ? -kBoxEps : kBoxEps) - r.camy) * invy : kInf;
                 const float kz = r.dz != 0.0f ? ((r.dz > 0.0f ? -kBoxEps : kBoxEps) - r.camz) * invz : kInf;
                 const int sxm = r.dx > 0.0f ? -1 : 0, sym = r.dy > 0.0f ? -1 : 0, szm = r.dz > 0.0f ? -1 : 0;
-                Stepper step;
-                step.init(a.inc);
-
                 float ray = r.t0, t_end = active ? r.t1 : -kInf;
                 // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (Stepper): cap j so that
                 // this drift stays below kBoxEps / 4, far inside the kBoxEps the skip regions are shrunk by.
@@ -766,8 +892,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                         t_end = fminf(t_end, tout + margin);
                         // jump to (at most) the last sample before tin - margin
                         while (ray < tin - margin - a.inc && ray < t_end) {
-                            const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, jump_cap));
-                            ray = step.advance(ray, want);
+                            const int want = max(1, min(__float2int_rd((tin - margin - ray) * inv_inc) - 1, jump_cap));
+                            ray = step_advance(s_steps, a.inc, ray, want);
                         }
                     }
                 }
@@ -812,8 +938,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                 float sgn = 0.0f, wx = 0.0f, wy = 0.0f, wz = 0.0f;
                                 const float px = __fmaf_rn(r.dx, ray, r.camx), py = __fmaf_rn(r.dy, ray, r.camy),
                                             pz = __fmaf_rn(r.dz, ray, r.camz);
-                                const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-                                const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
+                                // floor: one conversion on the address path (exact for every in-grid p; an out-of-range p
+                                // saturates and fails the bounds test below)
+                                const int ix = __float2int_rd(px), iy = __float2int_rd(py), iz = __float2int_rd(pz);
+                                const float fx = (float)ix, fy = (float)iy, fz = (float)iz;
                                 if (skip_ok && (unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
                                     (unsigned)iz < (unsigned)a.dimz) {
                                     // block map and cell class are fetched together (independent shared-memory addresses)
@@ -838,7 +966,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                             const float tz_ = __fmaf_rn((float)((iz & mask) + (size & szm)), invz, kz);
                                             const float tout = fminf(tx_, fminf(ty_, tz_));
                                             // steps to the first sample beyond the region's exit
-                                            const int n = max(1, min(__float2int_rd((tout - ray) * step.inv_inc) + 1, jump_cap));
+                                            const int n = max(1, min(__float2int_rd((tout - ray) * inv_inc) + 1, jump_cap));
                                             if (kind == kKindEmpty) {
                                                 // every sample before that one is invalid (kernel.cu:131,259)
                                                 act = kActJumpEmpty; nadv = n;
@@ -891,7 +1019,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                 } else if (act != kActJumpSame) {
                                     last_ok = false;  // :259 (invalid sample, or a run of them)
                                 }
-                                if (state == kMarch) ray = (nadv == 1) ? __fadd_rn(ray, a.inc) : step.advance(ray, nadv);  // :257,:260
+                                if (state == kMarch) ray = step_advance(s_steps, a.inc, ray, nadv);  // :257,:260
                             }
                         }
                     }
@@ -1067,7 +1195,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
             }
             tile = __shfl_sync(kFull, next, 0);
         }
-        if (a.maps_in_smem) {
+        if (kSmemMaps) {
             // every thread consumes this phase (a CTA must not retire, or refill, with a bulk copy in flight)
             if (!maps_ready) mbar_wait(mbar, phase);
             phase ^= 1u;
@@ -1432,19 +1560,33 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         CUDA_TRY(cudaGetLastError());
     }
     const size_t plane_stride = (size_t)p->num_chunks * L.bpc;
-    {
-        const dim3 cgrid((unsigned)((p->dimy * L.wpr + 7) / 8), (unsigned)p->dimz, (unsigned)p->num_chunks);
-        cell_class_kernel<<<cgrid, 256, 0, st>>>(dense, vbits, L.vpc, marks, plane_stride, p->dimz, p->dimy, p->dimx, L.wpr,
-                                                 L.nby, L.nbx, L.bpc);
-        CUDA_TRY(cudaGetLastError());
-        const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
-                  sbz = (L.nbz + kSuper - 1) / kSuper;
-        block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, plane_stride, bmap, L.bpc,
-                                                                                      L.nbz, L.nby, L.nbx, sbz, sby, sbx);
-        CUDA_TRY(cudaGetLastError());
-    }
     ForwardArgs a;
     memset(&a, 0, sizeof(a));
+    // shared-memory residency of one chunk's maps: class bit planes + block map + the block map builder's scratch
+    size_t tmp_bytes = 0;
+    {
+        int x = L.nbx, y = L.nby, z = L.nbz;
+        for (int l = 0; l < 3; l++) {
+            x = (x + 1) / 2; y = (y + 1) / 2; z = (z + 1) / 2;
+            tmp_bytes += (size_t)x * y * z;
+        }
+        tmp_bytes = align_up(tmp_bytes, 16);
+    }
+    const size_t map_bytes = L.vpc * sizeof(uint2) + L.bpc + tmp_bytes;
+    a.maps_in_smem = kFwdSmemFixed + map_bytes <= kFwdSmemMax;
+    {
+        const dim3 cgrid((unsigned)((L.nby * L.wpr + 3) / 4), (unsigned)L.nbz, (unsigned)p->num_chunks);
+        cell_class_kernel<<<cgrid, 128, 0, st>>>(dense, vbits, L.vpc, marks, plane_stride, p->dimz, p->dimy, p->dimx, L.wpr,
+                                                 L.nby, L.nbx, L.bpc);
+        CUDA_TRY(cudaGetLastError());
+        if (!a.maps_in_smem) {  // otherwise the forward CTAs build their chunk's block map in shared memory
+            const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
+                      sbz = (L.nbz + kSuper - 1) / kSuper;
+            block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, plane_stride, bmap, L.bpc,
+                                                                                          L.nbz, L.nby, L.nbx, sbz, sby, sbx);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
     a.sparse_mapping = sparse_mapping;
     a.vals_sdf = vals_sdf; a.vals_color = vals_color; a.vals_normal = vals_normal; a.vals_semantic = vals_semantic;
     a.view_matrix = view_matrix; a.intrinsics = intrinsics;
@@ -1452,8 +1594,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
     a.dense = dense; a.vbits = vbits; a.bmap = bmap; a.vpc = L.vpc; a.bpc = L.bpc; a.wpr = L.wpr;
-    const size_t map_bytes = L.vpc * sizeof(uint2) + L.bpc;
-    a.maps_in_smem = kFwdSmemFixed + map_bytes <= kFwdSmemMax;
+    a.marks = marks; a.plane_stride = plane_stride;
     a.tile_counter = (int32_t *)(ws + L.tiles_off);
     a.num_chunks = p->num_chunks;
     a.list_count = (int32_t *)(ws + L.head_off);
@@ -1477,7 +1618,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     // persistent: one CTA per SM (fewer when there is less than one tile per warp)
     const long long tiles_x = (p->width + kWarpW - 1) / kWarpW, tiles_y = (p->height + kWarpH - 1) / kWarpH;
     const long long all_tiles = ((tiles_x + 1) / 2) * ((tiles_y + 1) / 2) * 4 * p->views_per_chunk * p->num_chunks;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(sms, (all_tiles + kFwdWarps - 1) / kFwdWarps));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(sms, all_tiles));
     const size_t dyn = kFwdSmemFixed + (a.maps_in_smem ? map_bytes : 0);
     {
         static std::mutex mu;
@@ -1486,25 +1627,30 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         CUDA_TRY(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 0 || dev >= 64 || !configured[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    if (targets) {
-        {
-            ScopedKernelTimer timer(0, st);
-            raycast_forward_kernel<true><<<grid, kFwdThreads, dyn, st>>>(a);
+    {
+        ScopedKernelTimer timer(0, st);
+        if (targets) {
+            if (a.maps_in_smem) raycast_forward_kernel<true, true><<<grid, kFwdThreads, dyn, st>>>(a);
+            else raycast_forward_kernel<true, false><<<grid, kFwdThreads, dyn, st>>>(a);
+        } else {
+            if (a.maps_in_smem) raycast_forward_kernel<false, true><<<grid, kFwdThreads, dyn, st>>>(a);
+            else raycast_forward_kernel<false, false><<<grid, kFwdThreads, dyn, st>>>(a);
         }
-        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (targets) {
         finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
                                               targets->weight_semantic, targets->target_depth != nullptr,
                                               targets->target_color != nullptr, targets->target_label != nullptr);
-    } else {
-        ScopedKernelTimer timer(0, st);
-        raycast_forward_kernel<false><<<grid, kFwdThreads, dyn, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }
 
