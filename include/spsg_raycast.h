@@ -52,7 +52,8 @@ enum {
 enum {
     SPSG_FLAG_NO_CLIP = 1u << 0,       /* debug: march every sample like the reference (no ray/box clip)   */
     SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-block skipping                                    */
-    SPSG_FLAG_RECORD_HITS = 1u << 2    /* also write the per-pixel hit voxel index into the workspace       */
+    SPSG_FLAG_RECORD_HITS = 1u << 2,   /* also write the per-pixel hit voxel index into the workspace       */
+    SPSG_FLAG_GRADS_CLEARED = 1u << 3  /* backward only: rows [0,N) of d_* were cleared by the matching forward */
 };
 
 /* Replaces the reference's `opts` CPU tensor [W,H,depth_min,depth_max,thresh,ray_inc,Dx,Dy,Dz]
@@ -82,6 +83,18 @@ typedef struct spsg_loss_targets {
     float voxelsize;              /* depth scale applied to the rendering (train.py:635)              */
     float weight_depth, weight_color_loss, weight_semantic; /* loss = sum_k weight_k * loss_k         */
 } spsg_loss_targets;
+
+/* Optional argument of the indexed / fused forwards: the gradient buffers the matching backward will write.  When
+ * given, the forward's fill pass also clears their rows [0, N) (same launch, coalesced 16-byte stores), and the
+ * backward -- called with SPSG_FLAG_GRADS_CLEARED -- is a single gather launch that only touches voxels that received
+ * pixels.  Pass NULL when no backward will follow (the backward then clears the rows itself, like the reference's
+ * memsets at raycast_rgbd_cuda_kernel.cu:557-560). */
+typedef struct spsg_grad_buffers {
+    float *d_color;    /* (>=N,3)  */
+    float *d_depth;    /* (>=N,1)  */
+    float *d_normal;   /* (>=N,3)  */
+    float *d_semantic; /* (>=N,14) */
+} spsg_grad_buffers;
 
 /* Number of floats in the loss block written by spsg_raycast_forward_loss:
  * out[0]=depth L1  out[1]=colour L1  out[2]=semantic CE  out[3]=weight_depth*out[0]+weight_color_loss*out[1]+
@@ -126,8 +139,8 @@ SPSG_API int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t 
                                           const float *vals_semantic, const float *view_matrix,
                                           const float *intrinsics, float *image_color, float *image_depth,
                                           float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
-                                          int32_t *mapping3dto2d_num, void *workspace, size_t workspace_bytes,
-                                          void *stream);
+                                          int32_t *mapping3dto2d_num, const spsg_grad_buffers *clear_grads,
+                                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* == raycast_rgbd_cuda.backward (raycast_rgbd_cuda.cpp:102-140, raycast_rgbd_cuda_kernel.cu:365-423,
  *    535-586): d_x[v] = sum over views of mean over the first min(num, max_pixels) pixels registered to
@@ -155,7 +168,8 @@ SPSG_API int spsg_raycast_forward_loss(const spsg_raycast_params *p, int32_t *sp
                                        const float *intrinsics, float *image_color, float *image_depth,
                                        float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
                                        int32_t *mapping3dto2d_num, const spsg_loss_targets *t, float *loss_out,
-                                       void *workspace, size_t workspace_bytes, void *stream);
+                                       const spsg_grad_buffers *clear_grads, void *workspace, size_t workspace_bytes,
+                                       void *stream);
 
 /* Fused backward of the 2D losses through the raycast: the upstream gradient images are never
  * materialised; each registered pixel's gradient is recomputed from (rendering, target, loss_out).

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("SPSG_RAYCAST_LIB", os.path.join(_HERE, "lib", "libsps
 SPSG_FLAG_NO_CLIP = 1 << 0
 SPSG_FLAG_NO_BRICK_SKIP = 1 << 1
 SPSG_FLAG_RECORD_HITS = 1 << 2
+SPSG_FLAG_GRADS_CLEARED = 1 << 3
 SPSG_LOSS_OUT_FLOATS = 8
 
 # every symbol include/spsg_raycast.h declares (tests check the library exports them all)
@@ -47,6 +48,12 @@ class LossTargets(ctypes.Structure):
     ]
 
 
+class GradBuffers(ctypes.Structure):
+    """``spsg_grad_buffers``"""
+    _fields_ = [("d_color", ctypes.c_void_p), ("d_depth", ctypes.c_void_p), ("d_normal", ctypes.c_void_p),
+                ("d_semantic", ctypes.c_void_p)]
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
@@ -64,17 +71,17 @@ def _load():
     lib.spsg_workspace_bytes.argtypes = [pp]
     lib.spsg_build_index.restype = ctypes.c_int
     lib.spsg_build_index.argtypes = [vp, i64, vp, i32, i32, i32, i32, vp]
-    fwd = [pp] + [vp] * 14 + [vp, sz, vp]
+    gb = ctypes.POINTER(GradBuffers)
     lib.spsg_raycast_forward.restype = ctypes.c_int
-    lib.spsg_raycast_forward.argtypes = fwd
+    lib.spsg_raycast_forward.argtypes = [pp] + [vp] * 14 + [vp, sz, vp]
     lib.spsg_raycast_forward_indexed.restype = ctypes.c_int
-    lib.spsg_raycast_forward_indexed.argtypes = fwd
+    lib.spsg_raycast_forward_indexed.argtypes = [pp] + [vp] * 14 + [gb, vp, sz, vp]
     lib.spsg_raycast_backward.restype = ctypes.c_int
     lib.spsg_raycast_backward.argtypes = [pp] + [vp] * 11 + [vp, sz, vp]
     lib.spsg_raycast_occ.restype = ctypes.c_int
     lib.spsg_raycast_occ.argtypes = [pp, vp, vp, vp, vp, vp]
     lib.spsg_raycast_forward_loss.restype = ctypes.c_int
-    lib.spsg_raycast_forward_loss.argtypes = [pp] + [vp] * 14 + [lt, vp, vp, sz, vp]
+    lib.spsg_raycast_forward_loss.argtypes = [pp] + [vp] * 14 + [lt, vp, gb, vp, sz, vp]
     lib.spsg_raycast_backward_loss.restype = ctypes.c_int
     lib.spsg_raycast_backward_loss.argtypes = [pp, vp, vp, vp, lt, vp, vp] + [vp] * 7 + [vp, sz, vp]
     lib.spsg_timing_enable.restype = None
@@ -112,6 +119,10 @@ def workspace_bytes(params):
     if n == 0:
         raise SpsgError("spsg_workspace_bytes: %s" % lib.spsg_last_error().decode("utf-8", "replace"))
     return n
+
+
+def grad_buffers(d_color, d_depth, d_normal, d_semantic):
+    return GradBuffers(d_color.data_ptr(), d_depth.data_ptr(), d_normal.data_ptr(), d_semantic.data_ptr())
 
 
 def ptr(t):

@@ -97,7 +97,7 @@ struct Layout {
     size_t vbit_off, vbit_bytes;    // uint2 [B][vpc]: bit x of (.x, .y) = class of the sample cell whose corner (0,0,0)
                                     // is the voxel: 00 invalid, 10 positive, 01 negative, 11 mixed
     size_t bmap_off, bmap_bytes;    // u8  [B][bpc] block map
-    size_t marks_off, marks_bytes;  // u8  [3][B][bpc]: block holds a positive / negative / mixed cell
+    size_t marks_off, marks_bytes;  // u8  [B][bpc]: region bits of each 4^3 block (1 positive, 2 negative, 4 mixed cell)
     size_t zero_off, zero_bytes;    // everything from here to the list is cleared by the fill kernel of every forward
     size_t head_off;                // int32 list counter (256 B)
     size_t tiles_off, tiles_bytes;  // int32 [B] dynamic tile counters of the forward
@@ -128,7 +128,7 @@ Layout make_layout(const spsg_raycast_params *p) {
     L.bmap_bytes = align_up((size_t)p->num_chunks * L.bpc, 256);
     off += L.bmap_bytes;
     L.marks_off = off;
-    L.marks_bytes = align_up((size_t)3 * p->num_chunks * L.bpc, 256);
+    L.marks_bytes = align_up((size_t)p->num_chunks * L.bpc, 256);
     off += L.marks_bytes;
     L.zero_off = off;
     L.head_off = off;
@@ -388,17 +388,19 @@ __device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float 
 // per-call preparation: fill, index + dense brick, cell classes, block map
 // ---------------------------------------------------------------------------------------------
 
-// One launch instead of the reference's memsets (kernel.cu:475,483,515): up to three word-filled regions.
+// One launch instead of the reference's memsets (kernel.cu:475,483,515 and, when the gradient buffers are handed to
+// the forward, :557-560): up to kFillRegions word-filled regions.
+constexpr int kFillRegions = 7;
 struct FillArgs {
-    uint32_t *ptr[3];
-    size_t words[3];
-    uint32_t value[3];
+    uint32_t *ptr[kFillRegions];
+    size_t words[kFillRegions];
+    uint32_t value[kFillRegions];
 };
 
 __global__ void __launch_bounds__(256) fill_kernel(const FillArgs a) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < kFillRegions; r++) {
         uint32_t *p = a.ptr[r];
         const size_t n = a.words[r];
         if (!p || n == 0) continue;
@@ -442,12 +444,12 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
 //   mixed    all present, anything else: the value has to be computed.
 // Two bit planes per 32 cells of an x row (see Layout).  One warp per (4 y) x (4 z) x (32 x) slab, i.e. per run of
 // eight 4^3 blocks: it reads the 5 x 5 voxel rows once (all loads in flight together), emits the 16 class words and
-// -- being the only writer of those blocks -- their three marks (block holds a positive / negative / mixed cell).
+// -- being the only writer of those blocks -- their region bits (block holds a positive / negative / mixed cell).
 // grid = (ceil(nby*wpr / 4), nbz, B), block = 128.
 constexpr float kTiny = 1e-30f, kHuge = 3e38f;
 
 __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
-                                                         size_t vpc, uint8_t *__restrict__ marks, size_t plane_stride,
+                                                         size_t vpc, uint8_t *__restrict__ marks,
                                                          int dimz, int dimy, int dimx, int wpr, int nby, int nbx,
                                                          size_t bpc) {
     const unsigned kFull = 0xffffffffu;
@@ -500,13 +502,12 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
             if (lane == 0 && y < dimy && z < dimz)
                 vbits[(size_t)chunk * vpc + ((size_t)z * dimy + y) * wpr + xw] = make_uint2(v & ~vn, v & ~vp);
         }
-    if (lane < 24) {  // lanes 0-7: positive plane, 8-15: negative, 16-23: mixed; one block per lane
-        const int plane = lane >> 3, g = lane & 7;
-        const unsigned m = plane == 0 ? any_pos : plane == 1 ? any_neg : any_mix;
-        const int bx = xw * 8 + g;
+    if (lane < 8) {  // one block per lane: region bits 1 = holds a positive cell, 2 = negative, 4 = mixed
+        const int bx = xw * 8 + lane;
         if (bx < nbx)
-            marks[(size_t)plane * plane_stride + (size_t)chunk * bpc + ((size_t)zb * nby + yb) * nbx + bx] =
-                ((m >> (4 * g)) & 0xfu) ? 1 : 0;
+            marks[(size_t)chunk * bpc + ((size_t)zb * nby + yb) * nbx + bx] =
+                (uint8_t)((((any_pos >> (4 * lane)) & 0xfu) ? 1 : 0) | (((any_neg >> (4 * lane)) & 0xfu) ? 2 : 0) |
+                          (((any_mix >> (4 * lane)) & 0xfu) ? 4 : 0));
     }
 }
 
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
 //   positive / negative otherwise (two events: jump to the region's last sample, then step out);
 //   surface   (byte 0) if even the block itself is not uniform: samples there are classified cell by cell.
 // One CTA per 32^3-voxel super block (8^3 blocks).
-__global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restrict__ marks, size_t plane_stride,
+__global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restrict__ marks,
                                                         uint8_t *__restrict__ bmap, size_t bpc, int nbz, int nby,
                                                         int nbx, int sbz, int sby, int sbx) {
     __shared__ int agg8[64], agg16[8], agg32;
@@ -536,8 +537,7 @@ __global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restric
     const bool inside = fx < nbx && fy < nby && fz < nbz;
     const size_t at = (size_t)chunk * bpc + ((size_t)fz * nby + fy) * nbx + fx;
     int bits = 0;
-    if (inside)
-        bits = (marks[at] ? 1 : 0) | (marks[plane_stride + at] ? 2 : 0) | (marks[2 * plane_stride + at] ? 4 : 0);
+    if (inside) bits = marks[at];
     const int i8 = (tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1), i16 = (tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2);
     if (bits) {
         atomicOr(&agg8[i8], bits);
@@ -562,13 +562,13 @@ __global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restric
     }
 }
 
-// The same block map, built by a whole CTA straight into shared memory (forward prologue, when the chunk's maps are
-// shared-memory resident): region bits are OR-ed level by level, no atomics.  `bm` receives the map (nblocks bytes),
-// `tmp` needs n8 + n16 + n32 bytes.  Ends with a __syncthreads().
-__device__ __forceinline__ uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
+// The same block map, built in place by a whole CTA in shared memory (forward prologue, when the chunk's maps are
+// shared-memory resident): `bm` holds the blocks' region bits (nblocks bytes, as the classifier wrote them) and
+// receives the map; region bits are OR-ed level by level, no atomics.  `tmp` needs n8 + n16 + n32 bytes.  Every
+// thread of the CTA must call it; it starts and ends with a __syncthreads().
+__host__ __device__ constexpr uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
     const int r[5] = {0, r1, r2, r3, r4};
     int lu = 0, le = 0;
-#pragma unroll
     for (int l = 1; l <= 4; l++) {
         if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
         if (r[l] == 0) le = l;
@@ -578,6 +578,15 @@ __device__ __forceinline__ uint8_t block_map_byte(int r1, int r2, int r3, int r4
     return (uint8_t)((kind << 3) | lu);
 }
 
+// the same function as a table over the four 3-bit region words (r1 | r2 << 3 | r3 << 6 | r4 << 9)
+struct BlockLut { uint8_t v[4096]; };
+constexpr BlockLut make_block_lut() {
+    BlockLut t{};
+    for (int i = 0; i < 4096; i++) t.v[i] = block_map_byte(i & 7, (i >> 3) & 7, (i >> 6) & 7, (i >> 9) & 7);
+    return t;
+}
+__device__ const BlockLut kBlockLut = make_block_lut();
+
 __device__ __forceinline__ void decode3(int i, int nx, int ny, float inv_nx, float inv_ny, int &x, int &y, int &z) {
     // i = (z * ny + y) * nx + x for i < 2^22: quotients via fp32 reciprocals (exact after the +0.5 nudge)
     const int q = __float2int_rz(((float)i + 0.5f) * inv_nx);
@@ -586,21 +595,13 @@ __device__ __forceinline__ void decode3(int i, int nx, int ny, float inv_nx, flo
     y = q - z * ny;
 }
 
-__device__ void build_block_map_cta(const uint8_t *__restrict__ marks, size_t plane_stride, uint8_t *__restrict__ bm,
-                                    uint8_t *__restrict__ tmp, int nbx, int nby, int nbz, size_t bpc) {
+__device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restrict__ tmp, int nbx, int nby, int nbz) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int nblocks = nbx * nby * nbz;
     const int ax = (nbx + 1) >> 1, ay = (nby + 1) >> 1, az = (nbz + 1) >> 1;  // 8^3 regions
     const int cx = (ax + 1) >> 1, cy = (ay + 1) >> 1, cz = (az + 1) >> 1;  // 16^3
     const int ex = (cx + 1) >> 1, ey = (cy + 1) >> 1, ez = (cz + 1) >> 1;  // 32^3
     uint8_t *a8 = tmp, *a16 = a8 + ax * ay * az, *a32 = a16 + cx * cy * cz;
-    {
-        // region bits of the 4^3 blocks, four blocks per 32-bit word (marks are 0/1 bytes; bpc is a multiple of 16)
-        const uint32_t *m0 = reinterpret_cast<const uint32_t *>(marks), *m1 = reinterpret_cast<const uint32_t *>(marks + plane_stride),
-                       *m2 = reinterpret_cast<const uint32_t *>(marks + 2 * plane_stride);
-        uint32_t *bm32 = reinterpret_cast<uint32_t *>(bm);
-        for (int i = tid; i < (int)(bpc >> 2); i += T) bm32[i] = __ldg(m0 + i) | (__ldg(m1 + i) << 1) | (__ldg(m2 + i) << 2);
-    }
     __syncthreads();
     // each level: OR of the (up to) 2x2x2 children
     auto reduce = [&](const uint8_t *src, int sx, int sy, int sz, uint8_t *dst, int dx, int dy, int dz) {
@@ -621,12 +622,35 @@ __device__ void build_block_map_cta(const uint8_t *__restrict__ marks, size_t pl
     reduce(bm, nbx, nby, nbz, a8, ax, ay, az);
     reduce(a8, ax, ay, az, a16, cx, cy, cz);
     reduce(a16, cx, cy, cz, a32, ex, ey, ez);
-    const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
-    for (int i = tid; i < nblocks; i += T) {
-        int x, y, z;
-        decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
-        bm[i] = block_map_byte(bm[i], a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)],
-                               a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)], a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)]);
+    const uint8_t *__restrict__ lut = kBlockLut.v;
+    if ((nbx & 3) == 0) {
+        // four blocks of an x row per 32-bit word: they share their 16^3 / 32^3 regions and two 8^3 regions
+        const int wx = nbx >> 2;
+        const float inv_wx = 1.0f / (float)wx, inv_ny = 1.0f / (float)nby;
+        uint32_t *bm32 = reinterpret_cast<uint32_t *>(bm);
+        for (int i = tid; i < wx * nby * nbz; i += T) {
+            int xw, y, z;
+            decode3(i, wx, nby, inv_wx, inv_ny, xw, y, z);
+            const uint32_t w = bm32[i];
+            const int hi = ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + xw] << 6) |
+                           ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (xw >> 1)] << 9);
+            const uint8_t *p8 = a8 + ((z >> 1) * ay + (y >> 1)) * ax + 2 * xw;
+            const int lo0 = (int)p8[0] << 3, lo1 = (int)p8[1] << 3;  // nbx % 4 == 0: both 8^3 regions exist
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                out |= (uint32_t)__ldg(lut + (((w >> (8 * k)) & 7u) | (unsigned)(k < 2 ? lo0 : lo1) | (unsigned)hi)) << (8 * k);
+            bm32[i] = out;
+        }
+    } else {
+        const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
+        for (int i = tid; i < nblocks; i += T) {
+            int x, y, z;
+            decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
+            bm[i] = __ldg(lut + ((bm[i] & 7) | ((int)a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)] << 3) |
+                                 ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)] << 6) |
+                                 ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)] << 9)));
+        }
     }
     __syncthreads();
 }
@@ -667,8 +691,7 @@ struct ForwardArgs {
     const float *dense;
     const uint2 *vbits;   // [B][vpc]
     const uint8_t *bmap;  // [B][bpc]
-    const uint8_t *marks; // [3][B][bpc], plane stride below
-    size_t plane_stride;
+    const uint8_t *marks; // [B][bpc] region bits of the 4^3 blocks
     size_t vpc, bpc;
     int wpr;
     int maps_in_smem;
@@ -791,17 +814,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
 
     for (int chunk = blockIdx.x % a.num_chunks; chunk < a.num_chunks; chunk += gridDim.x) {
         if (kSmemMaps) {
-            if (threadIdx.x == 0) {  // cell classes: TMA bulk copies, completion on the mbarrier
-                const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2));
-                mbar_expect_tx(mbar, vb_bytes);
+            if (threadIdx.x == 0) {  // cell classes + the blocks' region bits: TMA bulk copies, completion on the mbarrier
+                const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2)), bm_bytes = (unsigned)a.bpc;
+                mbar_expect_tx(mbar, vb_bytes + bm_bytes);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(a.vbits + (size_t)chunk * a.vpc);
                 uint8_t *dst = reinterpret_cast<uint8_t *>(s_vbits);
                 for (unsigned o = 0; o < vb_bytes; o += 32768u) bulk_copy_g2s(dst + o, src + o, min(32768u, vb_bytes - o), mbar);
+                bulk_copy_g2s(s_bmap, a.marks + (size_t)chunk * a.bpc, bm_bytes, mbar);
             }
-            // block map: built here from the classifier's marks while the copy is in flight
-            build_block_map_cta(a.marks + (size_t)chunk * a.bpc, a.plane_stride, s_bmap, s_tmp, a.nbx, a.nby, a.nbz, a.bpc);
         }
-        bool maps_ready = !kSmemMaps;
         const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
         const uint8_t *bmap = kSmemMaps ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
         Volume v;
@@ -825,29 +846,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
             tile = __shfl_sync(kFull, t, 0);
         }
 
-        while (tile < total_tiles) {
-            int next = total_tiles;
-            if (lane == 0 && static_tiles < total_tiles) next = static_tiles + atomicAdd(counter, 1);  // prefetched
-
+        // Per-lane ray of the warp's current tile: set up (and clipped against the grid) before the chunk's maps are needed,
+        // so that the first tile's set-up overlaps the TMA copies.
+        struct TileRay {
+            Ray r;
+            float invx, invy, invz, kx, ky, kz;
+            int sxm, sym, szm;
+            float ray, t_end;
+            int jump_cap;
+            unsigned pix;
+            size_t gpix;
+            bool active, inside;
+            int img, view, wx0, wy0;
+#ifdef SPSG_STATS
+            long long clk0;
+#endif
+        };
+        auto prepare = [&](int tile, TileRay &q) {
             const int view = tile / tiles_per_image, tt = tile - view * tiles_per_image;
             const int blk = tt >> 2, sub = tt & 3;
             const int by = blk / blocks_x, bx = blk - by * blocks_x;
             const int wx0 = (bx * 2 + (sub & 1)) * kWarpW, wy0 = (by * 2 + (sub >> 1)) * kWarpH;
             const int img = chunk * a.views + view;
-            if (wx0 < a.width && wy0 < a.height) {
+            q.view = view; q.img = img; q.wx0 = wx0; q.wy0 = wy0;
+            q.inside = wx0 < a.width && wy0 < a.height;
+            if (q.inside) {
                 const unsigned ux = wx0 + (lane & 7), uy = wy0 + (lane >> 3);
                 const bool active = ux < (unsigned)a.width && uy < (unsigned)a.height;
                 const unsigned pix = uy * a.width + ux;
                 const size_t gpix = (size_t)img * a.width * a.height + pix;
 
-                int hit = -1;
-                float depth = 0.0f;
 #ifdef SPSG_STATS
-                const long long clk0 = clock64();
-                long long clk_march = 0, clk_refine = 0;
-                int my_iters = 0;
+                q.clk0 = clock64();
 #endif
-
                 // Lanes outside the image run the same loops below with an exhausted ray.
                 const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4,
                                         active ? ux : 0u, active ? uy : 0u, a.depth_min, a.depth_max);
@@ -897,16 +928,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                         }
                     }
                 }
+                q.r = r; q.invx = invx; q.invy = invy; q.invz = invz; q.kx = kx; q.ky = ky; q.kz = kz;
+                q.sxm = sxm; q.sym = sym; q.szm = szm; q.ray = ray; q.t_end = t_end; q.jump_cap = jump_cap;
+                q.pix = pix; q.gpix = gpix; q.active = active;
+            }
+        };
+        TileRay q;
+        q.inside = false;
+        if (tile < total_tiles) prepare(tile, q);
+        if (kSmemMaps) {
+            mbar_wait(mbar, phase);  // the chunk's class planes and region bits have landed
+            build_block_map_cta(s_bmap, s_tmp, a.nbx, a.nby, a.nbz);
+        }
 
+        while (tile < total_tiles) {
+            int next = total_tiles;
+            if (lane == 0 && static_tiles < total_tiles) next = static_tiles + atomicAdd(counter, 1);  // prefetched
+            if (q.inside) {
+                const Ray r = q.r;
+                const float invx = q.invx, invy = q.invy, invz = q.invz, kx = q.kx, ky = q.ky, kz = q.kz;
+                const int sxm = q.sxm, sym = q.sym, szm = q.szm, jump_cap = q.jump_cap;
+                float ray = q.ray;
+                const float t_end = q.t_end;
+                const unsigned pix = q.pix;
+                const size_t gpix = q.gpix;
+                const bool active = q.active;
+                const int img = q.img, view = q.view, wx0 = q.wx0, wy0 = q.wy0;
+                int hit = -1;
+                float depth = 0.0f;
 #ifdef SPSG_STATS
-                const long long clk1 = clock64();
-#endif
-                if (!maps_ready) {  // the chunk's maps have landed in shared memory
-                    mbar_wait(mbar, phase);
-                    maps_ready = true;
-                }
-#ifdef SPSG_STATS
-                const long long clk1b = clock64();
+                const long long clk0 = q.clk0;
+                long long clk_march = 0, clk_refine = 0;
+                int my_iters = 0;
+                const long long clk1 = clock64(), clk1b = clk1;
 #endif
 
                 // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the
@@ -1098,16 +1152,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                         const float2 t2 = __ldg(s2 + k);
                         sem[2 * k] = t2.x; sem[2 * k + 1] = t2.y;
                     }
-                    const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
-                    const int offset = atomicAdd(a.mapping3dto2d_num + row, 1);                            // :244
-                    if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;  // :245-247
-                    first = offset == 0;
                 }
+                {
+                    // voxel -> pixel registration (:244-247), one atomic per distinct voxel of the warp: lanes that hit
+                    // the same voxel take consecutive slots from a single atomicAdd (the reference's slot order is the
+                    // arbitrary order of its per-pixel atomics)
+                    const unsigned peers = __match_any_sync(kFull, hit);
+                    if (hit >= 0) {
+                        const int leader = __ffs(peers) - 1;
+                        const size_t row = (size_t)view * (size_t)a.num_locs + (size_t)hit;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(a.mapping3dto2d_num + row, __popc(peers));
+                        base = __shfl_sync(peers, base, leader);
+                        const int offset = base + __popc(peers & ((1u << lane) - 1));
+                        if (offset < a.max_pixels) a.mapping3dto2d[row * a.max_pixels + offset] = (int)pix;
+                        first = offset == 0;
+                    }
+                }
+#ifdef SPSG_STATS
+                // force the payload + atomic results before reading the clock
+                const long long clk_e1 = (col0 != 12345.0f && sem[13] != 12345.0f && !(first && dep == 54321.0f)) ? clock64() : 0;
+#endif
                 {
                     // the first pixel of a (voxel, view) pair appends the pair to the backward's work list (one atomic
                     // per warp)
                     const unsigned m = __ballot_sync(kFull, first);
+#ifdef SPSG_NO_LIST
+                    if (false) {
+#else
                     if (m) {
+#endif
                         int base = 0;
                         if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
                         base = __shfl_sync(kFull, base, 0);
@@ -1115,6 +1189,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                     }
                 }
                 if (a.hits && active) a.hits[gpix] = hit;
+#ifdef SPSG_STATS
+                const long long clk_e2 = clock64();
+#endif
 
                 if (kLoss) {
                     float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -1184,6 +1261,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                     STAT_ADD(18, clk_march); STAT_MAX(19, clk_march);            // march
                     STAT_ADD(20, clk_refine); STAT_MAX(21, clk_refine);          // refinement
                     STAT_ADD(22, clk3 - clk2); STAT_MAX(23, clk3 - clk2);        // epilogue
+                    STAT_ADD(40, clk_e1 - clk2); STAT_MAX(41, clk_e1 - clk2);    // payload + registration atomics
+                    STAT_ADD(42, clk_e2 - clk_e1); STAT_MAX(43, clk_e2 - clk_e1);  // list append
+                    STAT_ADD(44, clk3 - clk_e2); STAT_MAX(45, clk3 - clk_e2);    // staging + stores
                     STAT_ADD(24, clk3 - clk0); STAT_MAX(25, clk3 - clk0);        // whole tile
                     STAT_MAX(26, my_iters);
                     STAT_ADD(27, my_iters);
@@ -1194,10 +1274,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
 #endif
             }
             tile = __shfl_sync(kFull, next, 0);
+            if (tile < total_tiles) prepare(tile, q);
         }
         if (kSmemMaps) {
-            // every thread consumes this phase (a CTA must not retire, or refill, with a bulk copy in flight)
-            if (!maps_ready) mbar_wait(mbar, phase);
             phase ^= 1u;
             if (chunk + (int)gridDim.x < a.num_chunks) {
                 __syncthreads();  // all warps are done reading the maps before the next chunk's copy overwrites them
@@ -1245,24 +1324,32 @@ struct BackwardArgs {
     int vec4_ok;      // mapping3dto2d rows are 16-byte aligned
 };
 
-// Clears the 21 gradient slots of voxels [0, N) (replaces the 4 whole-buffer memsets of kernel.cu:557-560).
+// Clears the 21 gradient slots of voxels [0, N) (replaces the 4 whole-buffer memsets of kernel.cu:557-560): a warp
+// takes 32 consecutive voxels, so every store instruction writes one contiguous run of the AoS arrays.
 // kSkipHit (one view per chunk): rows of voxels that received pixels are left to the gather, which overwrites them.
 template <bool kSkipHit>
-__device__ __forceinline__ void zero_rows(const BackwardArgs &a, long long first, long long stride) {
-    for (long long i = first; i < a.num_locs; i += stride) {
-        if (kSkipHit && __ldg(a.mapping3dto2d_num + i) > 0) continue;
-        float *c = a.d_color + (size_t)i * 3, *n = a.d_normal + (size_t)i * 3;
-        c[0] = 0.0f; c[1] = 0.0f; c[2] = 0.0f;
-        n[0] = 0.0f; n[1] = 0.0f; n[2] = 0.0f;
-        a.d_depth[i] = 0.0f;
-        float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)i * 14);
-#pragma unroll
-        for (int k = 0; k < 7; k++) s[k] = make_float2(0.0f, 0.0f);
+__device__ __forceinline__ void zero_rows(const BackwardArgs &a, long long first_warp, long long num_warps) {
+    const int lane = threadIdx.x & 31;
+    for (long long base = first_warp * 32; base < a.num_locs; base += num_warps * 32) {
+        const long long i = base + lane;
+        const bool keep = kSkipHit && i < a.num_locs && __ldg(a.mapping3dto2d_num + i) > 0;
+        const unsigned kept = __ballot_sync(0xffffffffu, keep);
+        const int n = (int)min((long long)32, a.num_locs - base);
+        float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)base * 14);
+        for (int e = lane; e < n * 7; e += 32)
+            if (!((kept >> (e / 7)) & 1u)) s[e] = make_float2(0.0f, 0.0f);
+        float *c = a.d_color + (size_t)base * 3, *nm = a.d_normal + (size_t)base * 3;
+        for (int e = lane; e < n * 3; e += 32)
+            if (!((kept >> (e / 3)) & 1u)) {
+                c[e] = 0.0f;
+                nm[e] = 0.0f;
+            }
+        if (lane < n && !keep) a.d_depth[i] = 0.0f;
     }
 }
 
 __global__ void __launch_bounds__(256) backward_zero_kernel(const BackwardArgs a) {
-    zero_rows<false>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+    zero_rows<false>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)gridDim.x * blockDim.x) >> 5);
 }
 
 // Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal).
@@ -1342,7 +1429,7 @@ constexpr int kGatherWarps = 8;
 template <bool kFused, bool kAtomic>
 __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(const BackwardArgs a) {
     if ((int)blockIdx.x < a.zero_blocks) {
-        zero_rows<true>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)a.zero_blocks * blockDim.x);
+        zero_rows<true>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)a.zero_blocks * blockDim.x) >> 5);
         return;
     }
     __shared__ float s_g[kGatherWarps][32 * 21];
@@ -1509,8 +1596,8 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
                    const float *vals_sdf, const float *vals_color, const float *vals_normal,
                    const float *vals_semantic, const float *view_matrix, const float *intrinsics, float *image_color,
                    float *image_depth, float *image_normal, float *image_semantic, int32_t *mapping3dto2d,
-                   int32_t *mapping3dto2d_num, const spsg_loss_targets *targets, float *loss_out, void *workspace,
-                   size_t workspace_bytes, cudaStream_t st) {
+                   int32_t *mapping3dto2d_num, const spsg_loss_targets *targets, float *loss_out,
+                   const spsg_grad_buffers *clear_grads, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     if (int rc = check_params(p)) return rc;
     if (p->max_pixels_per_voxel <= 0) return fail(SPSG_ERR_INVALID_ARGUMENT, "max_pixels_per_voxel must be positive");
     if (!sparse_mapping || !view_matrix || !intrinsics || !image_color || !image_depth || !image_normal ||
@@ -1539,10 +1626,22 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         // sparse_mapping := -1 (kernel.cu:515), dense brick := NaN (0xffffffff: every voxel absent), block marks / list
         // counter / loss accumulators := 0 -- one launch
         FillArgs f;
+        memset(&f, 0, sizeof(f));
         f.ptr[0] = build_index ? (uint32_t *)sparse_mapping : nullptr; f.words[0] = cells; f.value[0] = 0xffffffffu;
         f.ptr[1] = (uint32_t *)dense; f.words[1] = L.dense_bytes / 4; f.value[1] = 0xffffffffu;
         f.ptr[2] = (uint32_t *)(ws + L.zero_off); f.words[2] = L.zero_bytes / 4; f.value[2] = 0u;
-        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4) / 4;
+        size_t grad_words = 0;
+        if (clear_grads && p->num_locs > 0) {  // rows [0, N) of the backward's outputs (kernel.cu:557-560)
+            if (!clear_grads->d_color || !clear_grads->d_depth || !clear_grads->d_normal || !clear_grads->d_semantic)
+                return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer in clear_grads");
+            const size_t n = (size_t)p->num_locs;
+            f.ptr[3] = (uint32_t *)clear_grads->d_semantic; f.words[3] = n * 14;
+            f.ptr[4] = (uint32_t *)clear_grads->d_color; f.words[4] = n * 3;
+            f.ptr[5] = (uint32_t *)clear_grads->d_normal; f.words[5] = n * 3;
+            f.ptr[6] = (uint32_t *)clear_grads->d_depth; f.words[6] = n;
+            grad_words = n * 21;
+        }
+        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4 + grad_words) / 4;
         const unsigned blocks = (unsigned)std::min<size_t>((vecs + 1023) / 1024 + 1, (size_t)sms * 8);
         fill_kernel<<<blocks, 256, 0, st>>>(f);
         CUDA_TRY(cudaGetLastError());
@@ -1559,7 +1658,6 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
                                                         p->dimx);
         CUDA_TRY(cudaGetLastError());
     }
-    const size_t plane_stride = (size_t)p->num_chunks * L.bpc;
     ForwardArgs a;
     memset(&a, 0, sizeof(a));
     // shared-memory residency of one chunk's maps: class bit planes + block map + the block map builder's scratch
@@ -1576,13 +1674,13 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.maps_in_smem = kFwdSmemFixed + map_bytes <= kFwdSmemMax;
     {
         const dim3 cgrid((unsigned)((L.nby * L.wpr + 3) / 4), (unsigned)L.nbz, (unsigned)p->num_chunks);
-        cell_class_kernel<<<cgrid, 128, 0, st>>>(dense, vbits, L.vpc, marks, plane_stride, p->dimz, p->dimy, p->dimx, L.wpr,
+        cell_class_kernel<<<cgrid, 128, 0, st>>>(dense, vbits, L.vpc, marks, p->dimz, p->dimy, p->dimx, L.wpr,
                                                  L.nby, L.nbx, L.bpc);
         CUDA_TRY(cudaGetLastError());
         if (!a.maps_in_smem) {  // otherwise the forward CTAs build their chunk's block map in shared memory
             const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
                       sbz = (L.nbz + kSuper - 1) / kSuper;
-            block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, plane_stride, bmap, L.bpc,
+            block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, bmap, L.bpc,
                                                                                           L.nbz, L.nby, L.nbx, sbz, sby, sbx);
             CUDA_TRY(cudaGetLastError());
         }
@@ -1594,7 +1692,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
     a.dense = dense; a.vbits = vbits; a.bmap = bmap; a.vpc = L.vpc; a.bpc = L.bpc; a.wpr = L.wpr;
-    a.marks = marks; a.plane_stride = plane_stride;
+    a.marks = marks;
     a.tile_counter = (int32_t *)(ws + L.tiles_off);
     a.num_chunks = p->num_chunks;
     a.list_count = (int32_t *)(ws + L.head_off);
@@ -1696,7 +1794,18 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     const long long max_items = p->num_locs * p->views_per_chunk;
     const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + kGatherWarps - 1) / kGatherWarps, (long long)sms * 8));
     const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 255) / 256, (long long)sms * 4);
-    if (p->views_per_chunk == 1) {
+    const bool cleared = (p->flags & SPSG_FLAG_GRADS_CLEARED) != 0;  // the forward's fill pass cleared rows [0, N)
+    if (cleared) {
+        a.zero_blocks = 0;
+        ScopedKernelTimer timer(1, st);
+        if (p->views_per_chunk == 1) {
+            if (fused) backward_gather_kernel<true, false><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+            else backward_gather_kernel<false, false><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        } else {
+            if (fused) backward_gather_kernel<true, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+            else backward_gather_kernel<false, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        }
+    } else if (p->views_per_chunk == 1) {
         // one launch: leading CTAs clear the rows of voxels nothing hit, the rest gather (plain stores)
         a.zero_blocks = (int)zero_blocks;
         ScopedKernelTimer timer(1, st);
@@ -1787,7 +1896,7 @@ int spsg_raycast_forward(const spsg_raycast_params *p, const int32_t *sparse_map
                          void *stream) {
     return launch_forward(p, false, const_cast<int32_t *>(sparse_mapping), locs, vals_sdf, vals_color, vals_normal,
                           vals_semantic, view_matrix, intrinsics, image_color, image_depth, image_normal,
-                          image_semantic, mapping3dto2d, mapping3dto2d_num, nullptr, nullptr, workspace,
+                          image_semantic, mapping3dto2d, mapping3dto2d_num, nullptr, nullptr, nullptr, workspace,
                           workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -1795,11 +1904,13 @@ int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t *sparse_m
                                  const float *vals_sdf, const float *vals_color, const float *vals_normal,
                                  const float *vals_semantic, const float *view_matrix, const float *intrinsics,
                                  float *image_color, float *image_depth, float *image_normal, float *image_semantic,
-                                 int32_t *mapping3dto2d, int32_t *mapping3dto2d_num, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
+                                 int32_t *mapping3dto2d, int32_t *mapping3dto2d_num,
+                                 const spsg_grad_buffers *clear_grads, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
     return launch_forward(p, true, sparse_mapping, locs, vals_sdf, vals_color, vals_normal, vals_semantic, view_matrix,
                           intrinsics, image_color, image_depth, image_normal, image_semantic, mapping3dto2d,
-                          mapping3dto2d_num, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+                          mapping3dto2d_num, nullptr, nullptr, clear_grads, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
 }
 
 int spsg_raycast_backward(const spsg_raycast_params *p, const float *grad_color, const float *grad_depth,
@@ -1835,11 +1946,12 @@ int spsg_raycast_forward_loss(const spsg_raycast_params *p, int32_t *sparse_mapp
                               const float *vals_semantic, const float *view_matrix, const float *intrinsics,
                               float *image_color, float *image_depth, float *image_normal, float *image_semantic,
                               int32_t *mapping3dto2d, int32_t *mapping3dto2d_num, const spsg_loss_targets *t,
-                              float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+                              float *loss_out, const spsg_grad_buffers *clear_grads, void *workspace,
+                              size_t workspace_bytes, void *stream) {
     if (!t) return fail(SPSG_ERR_INVALID_ARGUMENT, "loss targets are NULL");
     return launch_forward(p, true, sparse_mapping, locs, vals_sdf, vals_color, vals_normal, vals_semantic, view_matrix,
                           intrinsics, image_color, image_depth, image_normal, image_semantic, mapping3dto2d,
-                          mapping3dto2d_num, t, loss_out, workspace, workspace_bytes, (cudaStream_t)stream);
+                          mapping3dto2d_num, t, loss_out, clear_grads, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int spsg_raycast_backward_loss(const spsg_raycast_params *p, const float *image_color, const float *image_depth,

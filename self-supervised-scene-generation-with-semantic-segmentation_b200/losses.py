@@ -70,14 +70,17 @@ class FusedRaycastLossFunction(Function):
         dev = vals_sdf.device
         if getattr(m, "loss_out", None) is None:
             m.loss_out = torch.zeros(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+        # a backward will follow: let the forward's fill pass clear the gradient rows it will write
+        ctx.grads_cleared = any(ctx.needs_input_grad[2:6]) and n > 0
+        gb = N.grad_buffers(m.d_color, m.d_depth, m.d_normal, m.d_semantic) if ctx.grads_cleared else None
         with torch.cuda.device(dev):
             ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
             N.check(N.lib.spsg_raycast_forward_loss(
                 ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
                 N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
                 N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_normal), N.ptr(m.image_semantic),
-                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(m.loss_out), N.ptr(ws),
-                ws.numel(), rc._stream(dev)))
+                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(m.loss_out),
+                ctypes.byref(gb) if gb is not None else None, N.ptr(ws), ws.numel(), rc._stream(dev)))
         ctx.raycaster, ctx.params, ctx.targets, ctx.n = m, p, tg, n
         # keep the target tensors alive until backward (the struct only holds raw pointers)
         ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
@@ -94,6 +97,8 @@ class FusedRaycastLossFunction(Function):
     @staticmethod
     def backward(ctx, grad_total, grad_terms, *unused):
         m, p, tg, n = ctx.raycaster, ctx.params, ctx.targets, ctx.n
+        if ctx.grads_cleared:
+            p.flags |= N.SPSG_FLAG_GRADS_CLEARED
         dev = m.image_depth.device
         scale = grad_total.to(torch.float32).contiguous()
         with torch.cuda.device(dev):

@@ -36,11 +36,14 @@ class RayCastRGBDFunction(Function):
         num_locs = locs.shape[0]
         opts = [width, height, depth_min, depth_max, thresh_sample_dist, ray_increment, dims3d[2], dims3d[1],
                 dims3d[0]]  # raycast_rgbd.py:24-25
+        # a backward will follow: let the forward's fill pass clear the gradient rows it will write
+        ctx.grads_cleared = any(ctx.needs_input_grad[1:5])
         # construct_dense_sparse_mapping + forward (raycast_rgbd.py:23,26-28) as one native call
         raycast_rgbd_cuda.forward(sparse_mapping.to(device), locs.to(device), vals_sdf, vals_colors, vals_normals,
                                   vals_semantic, view_matrix_inv, image_color, image_depth, image_normal,
                                   image_semantic, mapping3dto2d, mapping3dto2d_num, intrinsic_params, opts,
-                                  views_per_chunk=views_per_chunk, flags=flags, build_index=True)
+                                  views_per_chunk=views_per_chunk, flags=flags, build_index=True,
+                                  clear_grads=(d_color, d_depth, d_normal, d_semantic) if ctx.grads_cleared else None)
         ctx.dims = [sparse_mapping.shape[0], dims3d[2], dims3d[1], dims3d[0], num_locs]  # raycast_rgbd.py:30-31
         ctx.views_per_chunk = views_per_chunk
         ctx.save_for_backward(sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color, d_depth, d_normal,
@@ -57,7 +60,7 @@ class RayCastRGBDFunction(Function):
         raycast_rgbd_cuda.backward(
             grad_color.contiguous(), grad_depth.contiguous(), grad_normal.contiguous(), grad_semantic.contiguous(),
             sparse_mapping, mapping3dto2d, mapping3dto2d_num, ctx.dims, d_color, d_depth, d_normal, d_semantic,
-            views_per_chunk=ctx.views_per_chunk)
+            views_per_chunk=ctx.views_per_chunk, grads_cleared=ctx.grads_cleared)
         # raycast_rgbd.py:42-43: (locs, vals_sdf, vals_colors, vals_normals, vals_semantic, None...)
         return (None, d_depth[:n], d_color[:n], d_normal[:n], d_semantic[:n]) + \
                (None,) * (len(ctx.needs_input_grad) - 5)

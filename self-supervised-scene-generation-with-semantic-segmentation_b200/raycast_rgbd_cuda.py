@@ -82,9 +82,10 @@ def _forward_params(sparse_mapping, locs, mapping3dto2d, opts, views_per_chunk=1
 
 def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_semantic, viewMatrixInv, imageColor,
             imageDepth, imageNormal, imageSemantic, mapping3dto2d, mapping3dto2d_num, intrinsicParams, opts,
-            views_per_chunk=1, flags=0, build_index=False):
-    """Reference signature (``raycast_color_forward``, raycast_rgbd_cuda.cpp:57-91) plus three keyword
-    extensions with reference-preserving defaults."""
+            views_per_chunk=1, flags=0, build_index=False, clear_grads=None):
+    """Reference signature (``raycast_color_forward``, raycast_rgbd_cuda.cpp:57-91) plus keyword extensions with
+    reference-preserving defaults.  ``clear_grads`` = (d_color, d_depth, d_normals, d_semantic) lets the forward's fill
+    pass clear the rows the matching ``backward(..., grads_cleared=True)`` will write (needs ``build_index=True``)."""
     for t, name in ((sparse_mapping, "sparse_mapping"), (locs, "locs"), (vals_sdf, "vals_sdf"),
                     (vals_color, "vals_color"), (vals_normals, "vals_normals"), (vals_semantic, "vals_semantic"),
                     (viewMatrixInv, "viewMatrixInv"), (imageColor, "imageColor"), (imageDepth, "imageDepth"),
@@ -119,16 +120,28 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
     with torch.cuda.device(dev):
         nbytes = N.workspace_bytes(p)
         ws = workspace(dev, nbytes, sparse_mapping)
-        fn = N.lib.spsg_raycast_forward_indexed if build_index else N.lib.spsg_raycast_forward
-        N.check(fn(ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
-                   N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(viewMatrixInv), N.ptr(intrinsicParams),
-                   N.ptr(imageColor), N.ptr(imageDepth), N.ptr(imageNormal), N.ptr(imageSemantic),
-                   N.ptr(mapping3dto2d), N.ptr(mapping3dto2d_num), N.ptr(ws), ws.numel(), _stream(dev)))
+        args = (ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
+                N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(viewMatrixInv), N.ptr(intrinsicParams),
+                N.ptr(imageColor), N.ptr(imageDepth), N.ptr(imageNormal), N.ptr(imageSemantic),
+                N.ptr(mapping3dto2d), N.ptr(mapping3dto2d_num))
+        if build_index:
+            gb = None
+            if clear_grads is not None:
+                for t, rows in zip(clear_grads, (3, 1, 3, 14)):
+                    _check_input(t, "clear_grads")
+                    if t.numel() < n * rows:
+                        raise RuntimeError("d_* buffers hold fewer than N = %d rows" % n)
+                gb = ctypes.byref(N.grad_buffers(*clear_grads))
+            N.check(N.lib.spsg_raycast_forward_indexed(*args, gb, N.ptr(ws), ws.numel(), _stream(dev)))
+        else:
+            if clear_grads is not None:
+                raise RuntimeError("clear_grads needs build_index=True")
+            N.check(N.lib.spsg_raycast_forward(*args, N.ptr(ws), ws.numel(), _stream(dev)))
     return ws
 
 
 def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping, mapping3dto2d, mapping3dto2d_num,
-             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1):
+             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1, grads_cleared=False):
     """Reference signature (``raycast_color_backward``, raycast_rgbd_cuda.cpp:102-140).
     ``dims`` = int32 CPU tensor (or sequence) [batch, Dx, Dy, Dz, N] (raycast_rgbd.py:30-31)."""
     for t, name in ((grad_color, "grad_color"), (grad_depth, "grad_depth"), (grad_normal, "grad_normal"),
@@ -143,7 +156,8 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
     p = N.make_params(width=grad_color.shape[2], height=grad_color.shape[1], depth_min=0, depth_max=0,
                       thresh_sample_dist=0, ray_increment=0, dimx=int(d[1]), dimy=int(d[2]), dimz=int(d[3]),
                       num_chunks=sparse_mapping.shape[0], views_per_chunk=views_per_chunk,
-                      max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n)
+                      max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n,
+                      flags=N.SPSG_FLAG_GRADS_CLEARED if grads_cleared else 0)
     dev = grad_color.device
     with torch.cuda.device(dev):
         ws = workspace(dev, N.workspace_bytes(p), sparse_mapping)
