@@ -963,10 +963,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                 const long long clk1 = clock64(), clk1b = clk1;
 #endif
 
-                // last valid sample (kernel.cu:64-69).  last_lazy: last_sdf is only a +-1 placeholder carrying the
-                // sign the cell class guarantees; the value is computed if and when a crossing needs it.
+                // last valid sample (kernel.cu:64-69).  "No valid last sample" is encoded as last_sdf == 0: a last value of
+                // +-0 can never satisfy the strict sign test (:205) either, so the two are indistinguishable.
+                // last_lazy: last_sdf is only a +-1 placeholder carrying the sign the cell class guarantees; the value
+                // is computed if and when a crossing needs it.
                 float last_sdf = 0.0f, last_alpha = 0.0f;
-                bool last_ok = false, last_lazy = false;
+                bool last_lazy = false;
                 float dist = 0.0f;
                 enum { kMarch = 0, kCross = 1, kDone = 2 };
                 int state = kMarch;
@@ -1010,8 +1012,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                         const int kind = b >> 3, size = 2 << (b & 7), mask = ~(size - 1);
                                         // a sign-uniform region cannot be jumped while the last valid sample has the
                                         // other sign: its first valid sample would be a crossing
-                                        const bool opposite = last_ok && ((kind == kKindPos && last_sdf < 0.0f) ||
-                                                                          (kind == kKindNeg && last_sdf > 0.0f));
+                                        const bool opposite = (kind == kKindPos && last_sdf < 0.0f) ||
+                                                              (kind == kKindNeg && last_sdf > 0.0f);
                                         if (!opposite) {
                                             // exit face per axis = origin + (dir > 0 ? size : 0), shrunk by kBoxEps (folded
                                             // into kx/ky/kz together with the camera position)
@@ -1047,7 +1049,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                                 if ((ca & cb) == 0u) {
                                                     sgn = ca ? 1.0f : -1.0f;
                                                     // opposite strict signs <=> last_sdf * (+-1) < 0 (last_sdf is never NaN)
-                                                    if (!(last_ok && __fmul_rn(last_sdf, sgn) < 0.0f)) act = kActSign;
+                                                    if (!(__fmul_rn(last_sdf, sgn) < 0.0f)) act = kActSign;
                                                 }
                                             }
                                         }
@@ -1061,17 +1063,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                                     } else {
                                         valid = sample_sdf(v, fast_ok, px, py, pz, dist);  // the reference's exact corner arithmetic
                                     }
-                                    if (valid && last_ok && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
+                                    if (valid && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
                                         state = kCross;
-                                    } else if (valid) {
-                                        last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
                                     } else {
-                                        last_ok = false;  // :259
+                                        last_sdf = valid ? dist : 0.0f; last_alpha = ray; last_lazy = false;  // :254-256 / :259
                                     }
                                 } else if (act == kActSign) {
-                                    last_sdf = sgn; last_alpha = ray; last_ok = true; last_lazy = true;  // :254-256
+                                    last_sdf = sgn; last_alpha = ray; last_lazy = true;  // :254-256
                                 } else if (act != kActJumpSame) {
-                                    last_ok = false;  // :259 (invalid sample, or a run of them)
+                                    last_sdf = 0.0f;  // :259 (invalid sample, or a run of them)
                                 }
                                 if (state == kMarch) ray = step_advance(s_steps, a.inc, ray, nadv);  // :257,:260
                             }
@@ -1119,8 +1119,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
                         if (hit >= 0) {
                             state = kDone;
                         } else {
-                            last_sdf = dist; last_alpha = ray; last_ok = true; last_lazy = false;  // :254-256
-                            ray = __fadd_rn(ray, a.inc);                                           // :257
+                            last_sdf = dist; last_alpha = ray; last_lazy = false;  // :254-256
+                            ray = __fadd_rn(ray, a.inc);                           // :257
                             state = kMarch;
                         }
                     }
