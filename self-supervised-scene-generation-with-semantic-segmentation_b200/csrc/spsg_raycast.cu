@@ -1432,46 +1432,54 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
         zero_rows<true>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)a.zero_blocks * blockDim.x) >> 5);
         return;
     }
-    __shared__ float s_g[kGatherWarps][32 * 21];
-    const unsigned kFull = 0xffffffffu;
+    // half a warp per item: 16 lanes cover the typical pixel count of a voxel, the two halves work on different items
+    __shared__ float s_g[kGatherWarps * 2][16 * 21];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *tile = s_g[warp];
-    const int warps_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps;
+    const int hl = lane & 15, half = lane >> 4;
+    const unsigned hmask = 0xffffu << (16 * half);
+    float *tile = s_g[warp * 2 + half];
+    const int groups_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps * 2;
     const int count = *a.list_count;
     const unsigned P = (unsigned)(a.width * a.height);
-    int item = ((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp;
+    int item = (((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp) * 2 + half;
     int2 e = item < count ? a.list[item] : make_int2(0, 0);
     while (item < count) {
         const int idx = e.x, img = e.y;
-        const int next_item = item + warps_total;
+        const int next_item = item + groups_total;
         if (next_item < count) e = a.list[next_item];  // prefetch the next pair
         const size_t row = (size_t)(img % a.views) * a.num_locs + idx;
         const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
         const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
         const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
         const float inv = __frcp_rn((float)max(cnt, 1));
-        float acc = 0.0f;
-        for (int k0 = 0; k0 < cnt; k0 += 32) {
-            const int m = min(32, cnt - k0);
-            if (lane < m) {
+        float acc0 = 0.0f, acc1 = 0.0f;  // channels hl and 16 + hl
+        for (int k0 = 0; k0 < cnt; k0 += 16) {
+            const int m = min(16, cnt - k0);
+            if (hl < m) {
                 float g[21];
-                pixel_grads<kFused>(a, pixbase + (unsigned)__ldg(prow + k0 + lane), g);
+                pixel_grads<kFused>(a, pixbase + (unsigned)__ldg(prow + k0 + hl), g);
 #pragma unroll
-                for (int c = 0; c < 21; c++) tile[lane * 21 + c] = g[c];
+                for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
             }
-            __syncwarp();
-            if (lane < 21)
-                for (int r = 0; r < m; r++) acc = __fmaf_rn(tile[r * 21 + lane], inv, acc);
-            __syncwarp();
+            __syncwarp(hmask);
+            for (int r = 0; r < m; r++) {
+                acc0 = __fmaf_rn(tile[r * 21 + hl], inv, acc0);
+                if (hl < 5) acc1 = __fmaf_rn(tile[r * 21 + 16 + hl], inv, acc1);
+            }
+            __syncwarp(hmask);
         }
-        float *dst = nullptr;
-        if (lane < 14) dst = a.d_semantic + (size_t)idx * 14 + lane;
-        else if (lane < 17) dst = a.d_color + (size_t)idx * 3 + (lane - 14);
-        else if (lane == 17) dst = a.d_depth + idx;
-        else if (lane < 21) dst = a.d_normal + (size_t)idx * 3 + (lane - 18);
-        if (dst) {
-            if (kAtomic) atomicAdd(dst, acc);
-            else *dst = acc;
+        // channel c -> destination: 0-13 semantic, 14-16 colour, 17 depth->sdf, 18-20 normal
+        float *d0 = hl < 14 ? a.d_semantic + (size_t)idx * 14 + hl : a.d_color + (size_t)idx * 3 + (hl - 14);
+        float *d1 = nullptr;
+        if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
+        else if (hl == 1) d1 = a.d_depth + idx;
+        else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
+        if (kAtomic) {
+            atomicAdd(d0, acc0);
+            if (d1) atomicAdd(d1, acc1);
+        } else {
+            *d0 = acc0;
+            if (d1) *d1 = acc1;
         }
         item = next_item;
     }
@@ -1790,9 +1798,9 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     a.num_locs = p->num_locs;
     a.vec4_ok = (p->max_pixels_per_voxel % 4 == 0) && aligned16(mapping3dto2d);
     const int sms = sm_count();
-    // one warp per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
+    // half a warp per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
     const long long max_items = p->num_locs * p->views_per_chunk;
-    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + kGatherWarps - 1) / kGatherWarps, (long long)sms * 8));
+    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + 2 * kGatherWarps - 1) / (2 * kGatherWarps), (long long)sms * 8));
     const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 255) / 256, (long long)sms * 4);
     const bool cleared = (p->flags & SPSG_FLAG_GRADS_CLEARED) != 0;  // the forward's fill pass cleared rows [0, N)
     if (cleared) {
