@@ -1288,18 +1288,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
 
 
 // loss_out[0..3] = depth, colour, semantic, weighted total; [4..6] = normalisers the backward needs.
-__global__ void finalize_loss_kernel(const double *__restrict__ acc, float *__restrict__ out, float w_depth,
-                                     float w_color, float w_sem, int has_depth, int has_color, int has_sem) {
+__global__ void __launch_bounds__(32) finalize_loss_kernel(const double *__restrict__ acc, float *__restrict__ out,
+                                                           float w_depth, float w_color, float w_sem, int has_depth,
+                                                           int has_color, int has_sem) {
+    // one warp: lane l sums slots l, l + 32, ...; xor-shuffle tree over the lanes (fixed order: deterministic)
+    const int lane = threadIdx.x;
     double t[6] = {0, 0, 0, 0, 0, 0};
-    for (int s = 0; s < kLossSlots; s++)
+    for (int s = lane; s < kLossSlots; s += 32)
+#pragma unroll
         for (int k = 0; k < 6; k++) t[k] += acc[s * 8 + k];
-    const float ld = has_depth ? (float)(t[0] / t[1]) : 0.0f;  // mean over an empty set is NaN, like torch.mean
-    const float lc = has_color ? (float)(t[2] / t[3]) : 0.0f;
-    const float ls = has_sem ? (float)(t[4] / t[5]) : 0.0f;
-    out[0] = ld; out[1] = lc; out[2] = ls;
-    out[3] = w_depth * ld + w_color * lc + w_sem * ls;
-    out[4] = (float)t[1]; out[5] = (float)t[3]; out[6] = (float)t[5];
-    out[7] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+    if (lane == 0) {
+        const float ld = has_depth ? (float)(t[0] / t[1]) : 0.0f;  // mean over an empty set is NaN, like torch.mean
+        const float lc = has_color ? (float)(t[2] / t[3]) : 0.0f;
+        const float ls = has_sem ? (float)(t[4] / t[5]) : 0.0f;
+        out[0] = ld; out[1] = lc; out[2] = ls;
+        out[3] = w_depth * ld + w_color * lc + w_sem * ls;
+        out[4] = (float)t[1]; out[5] = (float)t[3]; out[6] = (float)t[5];
+        out[7] = 0.0f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1355,8 +1365,20 @@ __global__ void __launch_bounds__(256) backward_zero_kernel(const BackwardArgs a
 // Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal).
 // Plain variant: read from the four gradient images.  Fused variant: recomputed from the rendering and the targets
 // of the 2D losses.
+// per-term factors of the fused variant: weight * upstream scale / normaliser (loss_out[4..6]), hoisted out of the pixels
+struct FusedCoef { float sem, col, dep; };
+
+__device__ __forceinline__ FusedCoef fused_coef(const BackwardArgs &a) {
+    FusedCoef c;
+    const float scale = a.grad_scale ? __ldg(a.grad_scale) : 1.0f;
+    c.dep = a.w_depth * a.loss.voxelsize * scale / a.loss_out[4];
+    c.col = a.w_color * scale / a.loss_out[5];
+    c.sem = a.w_sem * scale / a.loss_out[6];
+    return c;
+}
+
 template <bool kFused>
-__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix, float (&g)[21]) {
+__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCoef &fc, unsigned gpix, float (&g)[21]) {
     if (!kFused) {
         const float2 *s2 = reinterpret_cast<const float2 *>(a.grad_semantic + (size_t)gpix * 14);
 #pragma unroll
@@ -1370,7 +1392,6 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix
         g[18] = __ldg(n); g[19] = __ldg(n + 1); g[20] = __ldg(n + 2);
     } else {
         const LossArgs &L = a.loss;
-        const float scale = a.grad_scale ? __ldg(a.grad_scale) : 1.0f;
 #pragma unroll
         for (int k = 0; k < 21; k++) g[k] = 0.0f;
         // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
@@ -1394,9 +1415,9 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix
                     sum += l[k];
                 }
                 const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
-                const float f = a.w_sem * w, norm = a.loss_out[6];
+                const float f = fc.sem * w, inv_sum = 1.0f / sum;
 #pragma unroll
-                for (int k = 0; k < 14; k++) g[k] = f * (l[k] / sum - (k == y ? 1.0f : 0.0f)) / norm * scale;
+                for (int k = 0; k < 14; k++) g[k] = f * (l[k] * inv_sum - (k == y ? 1.0f : 0.0f));
             }
         }
         if (L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
@@ -1405,14 +1426,14 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix
             for (int k = 0; k < 3; k++) {
                 const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + (size_t)gpix * 3 + k), w),
                                           -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
-                g[14 + k] = a.w_color * ((d > 0.0f) - (d < 0.0f)) * w / a.loss_out[5] * scale;
+                g[14 + k] = fc.col * w * (float)((d > 0.0f) - (d < 0.0f));
             }
         }
         if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
             const float t = __ldg(L.target_depth + gpix);
             if (t != 0.0f) {
                 const float d = __fmul_rn(__ldg(a.image_depth + gpix), L.voxelsize) - t;
-                g[17] = a.w_depth * ((d > 0.0f) - (d < 0.0f)) * L.voxelsize / a.loss_out[4] * scale;
+                g[17] = fc.dep * (float)((d > 0.0f) - (d < 0.0f));
             }
         }
     }
@@ -1443,6 +1464,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
     const unsigned P = (unsigned)(a.width * a.height);
     int item = (((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp) * 2 + half;
     int2 e = item < count ? a.list[item] : make_int2(0, 0);
+    FusedCoef fc = {0.0f, 0.0f, 0.0f};
+    if (kFused) fc = fused_coef(a);
     while (item < count) {
         const int idx = e.x, img = e.y;
         const int next_item = item + groups_total;
@@ -1457,7 +1480,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
             const int m = min(16, cnt - k0);
             if (hl < m) {
                 float g[21];
-                pixel_grads<kFused>(a, pixbase + (unsigned)__ldg(prow + k0 + hl), g);
+                pixel_grads<kFused>(a, fc, pixbase + (unsigned)__ldg(prow + k0 + hl), g);
 #pragma unroll
                 for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
             }
@@ -1752,7 +1775,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     }
     CUDA_TRY(cudaGetLastError());
     if (targets) {
-        finalize_loss_kernel<<<1, 1, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
+        finalize_loss_kernel<<<1, 32, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
                                               targets->weight_semantic, targets->target_depth != nullptr,
                                               targets->target_color != nullptr, targets->target_label != nullptr);
         CUDA_TRY(cudaGetLastError());
