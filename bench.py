@@ -294,11 +294,15 @@ def roofline_ours(ctx, dev, steps):
     alg_bytes = 116 * ctx["nv"] + 84 * ctx["rays"]
     us = f_ms / max(f_n, 1) * 1e3
     achieved = alg_bytes / (us * 1e-6) / 1e9 if us > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed ncu --set full captures
+    # (profiles/r01_c2_ncu_full_summary.md, r01_c3_ncu_full_summary.md); in C2 the 6.9 MB of images are still dirty
+    # in the 126 MB L2 when the kernel ends, so only the reads show up
+    traffic = {1: 2.85e6, 40: 319.1e6}.get(ctx["rays"] // (ctx["S"].WIDTH * ctx["S"].HEIGHT))
     return {"bound": "hbm", "kernel": "raycast_forward_kernel", "achieved": round(achieved, 1), "peak": peak,
-            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": which,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": round(us, 2),
             "backward_gather_us": round(g_ms / max(g_n, 1) * 1e3, 2),
-            "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 5 and profiles/"}
+            "note": "not HBM-bound (traffic <= algorithmic bytes): instruction issue (C3) / dependent latency (C2), see DESIGN.md section 5 and profiles/README.md"}
 
 
 def cpu_baseline(B, F, seconds=12.0):
