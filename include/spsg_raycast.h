@@ -182,6 +182,22 @@ SPSG_API int spsg_raycast_backward_loss(const spsg_raycast_params *p, const floa
                                         float *d_normal, float *d_semantic, void *workspace, size_t workspace_bytes,
                                         void *stream);
 
+/* == loss.compute_normals_sparse (reference torch/loss.py:285-306, with compute_normals_dense :261-267): per-voxel
+ *    normals of the sparse SDF, the producer of the raycaster's vals_normals (train.py:542).  normals[i] =
+ *    -normalize(R_chunk * central_difference(sdf at voxel i), eps 1e-5); absent neighbours count as 0, voxels on the
+ *    volume border get 0.  transform: (B,4,4) row-major (its upper-left 3x3 is R) or NULL.  `index` is caller-owned
+ *    scratch of B*Dz*Dy*Dx int32 (the voxel index, same content as sparse_mapping); the forward fills it, the
+ *    backward reads it.  One fill + one scatter + one gather launch; no dense volumes, no per-chunk host loop. */
+SPSG_API int spsg_normals_forward(const int64_t *locs, int64_t num_locs, const float *vals_sdf, const float *transform,
+                                  int32_t *index, int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx,
+                                  float *normals, void *stream);
+
+/* Gradient of the above w.r.t. vals_sdf: d_sdf (N,1) is fully written.  scratch_u: N*3 floats of caller-owned
+ *    scratch.  Two gather launches, deterministic (no atomics). */
+SPSG_API int spsg_normals_backward(const int64_t *locs, int64_t num_locs, const float *vals_sdf, const float *transform,
+                                   const int32_t *index, int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx,
+                                   const float *grad_normals, float *scratch_u, float *d_sdf, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
