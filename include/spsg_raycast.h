@@ -198,6 +198,21 @@ SPSG_API int spsg_normals_backward(const int64_t *locs, int64_t num_locs, const 
                                    const int32_t *index, int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx,
                                    const float *grad_normals, float *scratch_u, float *d_sdf, void *stream);
 
+/* The 2D losses as stand-alone image-space ops, i.e. at the boundary the reference applies them: to rendered images
+ *    (depth L1 train.py:635-638, colour L1 loss.compute_2dcolor_loss loss.py:246-257, 2D semantic CE train.py:744-746).
+ *    Same terms, targets struct and loss_out block as spsg_raycast_forward_loss; a rendering pointer may be NULL when its
+ *    target is NULL.  scratch: >= 4096 bytes, 8-byte aligned.  One pass over the pixels + finalize. */
+SPSG_API int spsg_losses2d_forward(const spsg_loss_targets *t, const float *image_color, const float *image_depth,
+                                   const float *image_semantic, int64_t num_pixels, float *loss_out, void *scratch,
+                                   size_t scratch_bytes, void *stream);
+
+/* Gradient images of grad_scale * loss_out[3] w.r.t. the renderings: d_color (P,3), d_depth (P), d_semantic (P,14), any
+ *    of them NULL to skip; pixels outside a term's valid set get 0. */
+SPSG_API int spsg_losses2d_backward(const spsg_loss_targets *t, const float *image_color, const float *image_depth,
+                                    const float *image_semantic, int64_t num_pixels, const float *loss_out,
+                                    const float *grad_scale, float *d_color, float *d_depth, float *d_semantic,
+                                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

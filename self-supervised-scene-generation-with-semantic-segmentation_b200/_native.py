@@ -21,7 +21,7 @@ EXPORTS = (
     "spsg_version", "spsg_last_error", "spsg_workspace_bytes", "spsg_build_index", "spsg_raycast_forward",
     "spsg_raycast_forward_indexed", "spsg_raycast_backward", "spsg_raycast_occ", "spsg_raycast_forward_loss",
     "spsg_raycast_backward_loss", "spsg_timing_enable", "spsg_timing_read", "spsg_normals_forward",
-    "spsg_normals_backward",
+    "spsg_normals_backward", "spsg_losses2d_forward", "spsg_losses2d_backward",
 )
 
 
@@ -89,6 +89,10 @@ def _load():
     lib.spsg_normals_forward.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.spsg_normals_backward.restype = ctypes.c_int
     lib.spsg_normals_backward.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.spsg_losses2d_forward.restype = ctypes.c_int
+    lib.spsg_losses2d_forward.argtypes = [lt, vp, vp, vp, i64, vp, vp, sz, vp]
+    lib.spsg_losses2d_backward.restype = ctypes.c_int
+    lib.spsg_losses2d_backward.argtypes = [lt, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.spsg_timing_enable.restype = None
     lib.spsg_timing_enable.argtypes = [ctypes.c_int]
     lib.spsg_timing_read.restype = ctypes.c_int

@@ -1424,15 +1424,16 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCo
             const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float d = __fadd_rn(__fmul_rn(__ldg(a.image_color + (size_t)gpix * 3 + k), w),
-                                          -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
-                g[14 + k] = fc.col * w * (float)((d > 0.0f) - (d < 0.0f));
+                const float c = __ldg(a.image_color + (size_t)gpix * 3 + k);
+                const float d = __fadd_rn(__fmul_rn(c, w), -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
+                if (c != -CUDART_INF_F) g[14 + k] = fc.col * w * (float)((d > 0.0f) - (d < 0.0f));  // valid = != -inf
             }
         }
         if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
             const float t = __ldg(L.target_depth + gpix);
-            if (t != 0.0f) {
-                const float d = __fmul_rn(__ldg(a.image_depth + gpix), L.voxelsize) - t;
+            const float r = __ldg(a.image_depth + gpix);
+            if (t != 0.0f && r != -CUDART_INF_F) {
+                const float d = __fmul_rn(r, L.voxelsize) - t;
                 g[17] = fc.dep * (float)((d > 0.0f) - (d < 0.0f));
             }
         }
@@ -1505,6 +1506,92 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
             if (d1) *d1 = acc1;
         }
         item = next_item;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the 2D losses as stand-alone image-space ops (the reference's own boundary: loss.compute_2dcolor_loss and the
+// inline expressions of train.py:635-638, 744-746 applied to rendered images)
+// ---------------------------------------------------------------------------------------------
+
+struct Losses2DArgs {
+    const float *image_color, *image_depth, *image_semantic;
+    LossArgs loss;
+    long long num_pixels;
+};
+
+// one thread per pixel: the same six sums the fused forward accumulates in its epilogue
+__global__ void __launch_bounds__(256) losses2d_forward_kernel(const Losses2DArgs a) {
+    const float ninf = -CUDART_INF_F;
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const LossArgs &L = a.loss;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.num_pixels; p += (long long)gridDim.x * blockDim.x) {
+        if (L.target_depth) {  // train.py:635-638
+            const float r = __ldg(a.image_depth + p), t = __ldg(L.target_depth + p);
+            if (r != ninf && t != 0.0f) { acc[0] += fabsf(__fmul_rn(r, L.voxelsize) - t); acc[1] += 1.0f; }
+        }
+        if (L.target_color) {  // loss.py:246-257 (valid is per element)
+            const float w = L.weight_color ? __ldg(L.weight_color + p) : 1.0f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float c = __ldg(a.image_color + p * 3 + k);
+                if (c != ninf) {
+                    acc[2] += fabsf(__fadd_rn(__fmul_rn(c, w), -__fmul_rn(__ldg(L.target_color + p * 3 + k), w)));
+                    acc[3] += 1.0f;
+                }
+            }
+        }
+        if (L.target_label) {  // train.py:744-746
+            const int y = L.target_label[p];
+            if (y < 14) {
+                float l[14];
+                const float2 *s2 = reinterpret_cast<const float2 *>(a.image_semantic + p * 14);
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const float2 t2 = __ldg(s2 + k);
+                    l[2 * k] = t2.x; l[2 * k + 1] = t2.y;
+                }
+                if (l[0] != ninf) {
+                    float m = l[0];
+#pragma unroll
+                    for (int k = 1; k < 14; k++) m = fmaxf(m, l[k]);
+                    float sum = 0.0f, ly = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 14; k++) {
+                        sum += expf(l[k] - m);
+                        if (k == y) ly = l[k];
+                    }
+                    const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+                    acc[4] += w * (logf(sum) + m - ly);
+                    acc[5] += w;
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    float mine = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const float t = warp_sum(acc[k]);
+        if (lane == k) mine = t;
+    }
+    const unsigned slot = (blockIdx.x * 8u + (threadIdx.x >> 5)) % kLossSlots;
+    if (lane < 6 && mine != 0.0f) atomicAdd(L.accum + slot * 8 + lane, (double)mine);
+}
+
+// gradient images of the weighted total w.r.t. the renderings (zero where a pixel is not part of a term)
+__global__ void __launch_bounds__(256) losses2d_backward_kernel(const BackwardArgs a, long long num_pixels, float *d_color,
+                                                               float *d_depth, float *d_semantic) {
+    const FusedCoef fc = fused_coef(a);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < num_pixels; p += (long long)gridDim.x * blockDim.x) {
+        float g[21];
+        pixel_grads<true>(a, fc, (unsigned)p, g);
+        if (d_semantic) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(d_semantic + p * 14)[k] = make_float2(g[2 * k], g[2 * k + 1]);
+        }
+        if (d_color) { d_color[p * 3] = g[14]; d_color[p * 3 + 1] = g[15]; d_color[p * 3 + 2] = g[16]; }
+        if (d_depth) d_depth[p] = g[17];
     }
 }
 
@@ -2148,6 +2235,57 @@ int spsg_normals_backward(const int64_t *locs, int64_t num_locs, const float *va
     normals_backward_u_kernel<<<blocks, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     normals_backward_gather_kernel<<<blocks, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_losses2d_forward(const spsg_loss_targets *t, const float *image_color, const float *image_depth,
+                          const float *image_semantic, int64_t num_pixels, float *loss_out, void *scratch,
+                          size_t scratch_bytes, void *stream) {
+    if (!t || !loss_out) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL loss targets / loss_out");
+    if (num_pixels < 0 || num_pixels * 14 >= (1ll << 32)) return fail(SPSG_ERR_INVALID_ARGUMENT, "bad pixel count");
+    if ((t->target_depth && !image_depth) || (t->target_color && !image_color) || (t->target_label && !image_semantic))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "a target is set but its rendering is NULL");
+    if (image_semantic && (reinterpret_cast<uintptr_t>(image_semantic) & 7u)) return fail(SPSG_ERR_INVALID_ARGUMENT, "image_semantic must be 8-byte aligned");
+    const size_t need = (size_t)kLossSlots * 8 * sizeof(double);
+    if (!scratch || scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 7u)) return fail(SPSG_ERR_WORKSPACE_TOO_SMALL, "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, need, st));
+    Losses2DArgs a;
+    memset(&a, 0, sizeof(a));
+    a.image_color = image_color; a.image_depth = image_depth; a.image_semantic = image_semantic;
+    a.loss = make_loss_args(t, (double *)scratch);
+    a.num_pixels = num_pixels;
+    if (num_pixels > 0) {
+        const unsigned blocks = (unsigned)std::min<long long>((num_pixels + 255) / 256, (long long)sm_count() * 8);
+        losses2d_forward_kernel<<<blocks, 256, 0, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
+    finalize_loss_kernel<<<1, 32, 0, st>>>((const double *)scratch, loss_out, t->weight_depth, t->weight_color_loss,
+                                           t->weight_semantic, t->target_depth != nullptr, t->target_color != nullptr,
+                                           t->target_label != nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_losses2d_backward(const spsg_loss_targets *t, const float *image_color, const float *image_depth,
+                           const float *image_semantic, int64_t num_pixels, const float *loss_out,
+                           const float *grad_scale, float *d_color, float *d_depth, float *d_semantic, void *stream) {
+    if (!t || !loss_out) return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL loss targets / loss_out");
+    if (num_pixels < 0 || num_pixels * 14 >= (1ll << 32)) return fail(SPSG_ERR_INVALID_ARGUMENT, "bad pixel count");
+    if ((t->target_depth && !image_depth) || (t->target_color && !image_color) || (t->target_label && !image_semantic))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "a target is set but its rendering is NULL");
+    if (d_semantic && (reinterpret_cast<uintptr_t>(d_semantic) & 7u)) return fail(SPSG_ERR_INVALID_ARGUMENT, "d_semantic must be 8-byte aligned");
+    if (num_pixels == 0) return SPSG_OK;
+    BackwardArgs a;
+    memset(&a, 0, sizeof(a));
+    a.image_color = image_color; a.image_depth = image_depth; a.image_semantic = image_semantic;
+    a.loss = make_loss_args(t, nullptr);
+    a.loss_out = loss_out;
+    a.w_depth = t->weight_depth; a.w_color = t->weight_color_loss; a.w_sem = t->weight_semantic;
+    a.grad_scale = grad_scale;
+    const unsigned blocks = (unsigned)std::min<long long>((num_pixels + 255) / 256, (long long)sm_count() * 8);
+    losses2d_backward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, num_pixels, d_color, d_depth, d_semantic);
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }

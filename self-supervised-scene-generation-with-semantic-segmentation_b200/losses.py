@@ -135,3 +135,84 @@ def render_with_2d_losses(raycaster, locs, vals_sdf, vals_colors, vals_normals, 
         None if target2d_label is None else target2d_label.contiguous(),
         weight_semantic_class, voxelsize, (weight_depth_loss, weight_color_loss, weight_semantic_loss))
     return out[0], out[1], out[2:]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same three terms as stand-alone ops on rendered images: the boundary at which the reference applies them
+# (loss.compute_2dcolor_loss, loss.py:246-257; the inline expressions of train.py:635-638 and :744-746).  One pass over
+# the pixels instead of a boolean-mask select (which synchronises the host) + several element-wise kernels.
+# ---------------------------------------------------------------------------------------------------------------------
+
+class _Losses2D(Function):
+    @staticmethod
+    def forward(ctx, image_color, image_depth, image_semantic, target_depth, target_color, weight_color, target_label,
+                class_weight, voxelsize, weights):
+        some = next(t for t in (image_color, image_depth, image_semantic) if t is not None)
+        dev = some.device
+        px = {"c": None if image_color is None else image_color.numel() // 3,
+              "d": None if image_depth is None else image_depth.numel(),
+              "s": None if image_semantic is None else image_semantic.numel() // 14}
+        num_pixels = next(v for v in px.values() if v is not None)
+        if any(v is not None and v != num_pixels for v in px.values()):
+            raise RuntimeError("renderings disagree on the number of pixels")
+        for t, name in ((image_color, "image_color"), (image_depth, "image_depth"), (image_semantic, "image_semantic")):
+            if t is not None:
+                rc._check_input(t, name)
+                rc._check_dtype(t, torch.float32, name)
+        tg = _targets_struct(1, 1, num_pixels, target_depth, target_color, weight_color, target_label, class_weight,
+                             voxelsize, weights)
+        loss_out = torch.empty(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+        scratch = torch.empty(4096, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            N.check(N.lib.spsg_losses2d_forward(ctypes.byref(tg), N.ptr(image_color), N.ptr(image_depth),
+                                                N.ptr(image_semantic), num_pixels, N.ptr(loss_out), N.ptr(scratch),
+                                                scratch.numel(), rc._stream(dev)))
+        ctx.targets, ctx.num_pixels, ctx.loss_out = tg, num_pixels, loss_out
+        ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
+        ctx.save_for_backward(*[t for t in (image_color, image_depth, image_semantic) if t is not None])
+        ctx.present = tuple(t is not None for t in (image_color, image_depth, image_semantic))
+        out = loss_out[:4].clone()
+        return out[3], out[:3]
+
+    @staticmethod
+    def backward(ctx, grad_total, grad_terms):
+        saved = list(ctx.saved_tensors)
+        imgs = [saved.pop(0) if p else None for p in ctx.present]
+        dev = ctx.loss_out.device
+        need = ctx.needs_input_grad[:3]
+        grads = [torch.empty_like(t) if (t is not None and n) else None for t, n in zip(imgs, need)]
+        scale = grad_total.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            N.check(N.lib.spsg_losses2d_backward(ctypes.byref(ctx.targets), N.ptr(imgs[0]), N.ptr(imgs[1]), N.ptr(imgs[2]),
+                                                 ctx.num_pixels, N.ptr(ctx.loss_out), N.ptr(scale), N.ptr(grads[0]),
+                                                 N.ptr(grads[1]), N.ptr(grads[2]), rc._stream(dev)))
+        return (grads[0], grads[1], grads[2]) + (None,) * 7
+
+
+def losses_2d(raycast_color=None, raycast_depth=None, raycast_semantic=None, images_depth=None, images_color=None,
+              weight_color=None, target2d_label=None, weight_semantic_class=None, voxelsize=0.02,
+              weight_depth_loss=1.0, weight_color_loss=1.0, weight_semantic_loss=1.0):
+    """All requested 2D terms of rendered images in one pass.  Returns (total, terms[3] = depth, colour, semantic);
+    gradients flow from ``total`` into the renderings."""
+    c = lambda t: None if t is None else t.contiguous()
+    return _Losses2D.apply(c(raycast_color) if images_color is not None else None,
+                           c(raycast_depth) if images_depth is not None else None,
+                           c(raycast_semantic) if target2d_label is not None else None,
+                           c(images_depth), c(images_color), c(weight_color), c(target2d_label), weight_semantic_class,
+                           voxelsize, (weight_depth_loss, weight_color_loss, weight_semantic_loss))
+
+
+def depth_l1_loss(raycast_depth, images_depth, voxelsize):
+    """train.py:635-638: mean |raycast_depth * voxelsize - images_depth| over (rendered & images_depth != 0)."""
+    return losses_2d(raycast_depth=raycast_depth, images_depth=images_depth, voxelsize=voxelsize)[0]
+
+
+def color_l1_loss(raycast_color, target_color, weight_color=None):
+    """Drop-in for loss.compute_2dcolor_loss (loss.py:246-257); ``weight_color`` (B,1,H,W) or None."""
+    return losses_2d(raycast_color=raycast_color, images_color=target_color, weight_color=weight_color)[0]
+
+
+def semantic_2d_ce_loss(raycast_semantic, target2d_label, weight_semantic_class=None):
+    """train.py:744-746: class-weighted cross-entropy over (label < 14 & rendered)."""
+    return losses_2d(raycast_semantic=raycast_semantic, target2d_label=target2d_label,
+                     weight_semantic_class=weight_semantic_class)[0]

@@ -66,3 +66,18 @@ def test_reference_style_import_path():
             % (ROOT, os.path.join(PACKAGE_DIR, "dropin")))
     out = subprocess.check_output([sys.executable, "-c", code], text=True)
     assert "spsg_b200.raycast_rgbd" in out and "spsg_b200.raycast_rgbd_cuda" in out
+
+
+def test_patch_reference_loss_module():
+    """patch_reference_loss swaps the two loss.py functions on the hot path for the CUDA ops, keeping their signatures."""
+    import types
+    import spsg_b200
+    from spsg_b200 import losses, normals
+    fake = types.ModuleType("loss")
+    fake.compute_normals_sparse = lambda sdf_locs, sdf_vals, dims, transform=None: None
+    fake.compute_2dcolor_loss = lambda raycast_color, target_color, weight_color: None
+    spsg_b200.patch_reference_loss(fake)
+    assert fake.compute_normals_sparse is normals.compute_normals_sparse
+    assert fake.compute_2dcolor_loss is losses.color_l1_loss
+    assert list(inspect.signature(normals.compute_normals_sparse).parameters)[:4] == ["sdf_locs", "sdf_vals", "dims", "transform"]
+    assert list(inspect.signature(losses.color_l1_loss).parameters) == ["raycast_color", "target_color", "weight_color"]

@@ -96,3 +96,53 @@ def test_fused_loss_terms_can_be_switched_off(cuda_device):
     assert float(terms[1]) == 0.0 and float(terms[2]) == 0.0
     total.backward()
     assert float(sdf.grad.abs().sum()) > 0
+
+
+def test_fused_colour_loss_matches_reference_python_golden(cuda_device):
+    """The fused colour-L1 term against the value the reference's own loss.compute_2dcolor_loss produced
+    (tests/golden/losses_ref.npz): the golden rendering (with -inf holes) is reproduced by a one-voxel-per-pixel scene is
+    not possible, so the term is checked through the un-fused product path: spsg_b200.losses.color_l1_loss."""
+    import os
+    from spsg_b200.losses import color_l1_loss
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "losses_ref.npz"))
+    pred = torch.from_numpy(g["c_pred"]).to(cuda_device)
+    tgt = torch.from_numpy(g["c_tgt"]).to(cuda_device)
+    for name, ww in (("color_w", torch.from_numpy(g["c_weight"]).to(cuda_device)), ("color_now", None)):
+        p = pred.clone().requires_grad_(True)
+        l = color_l1_loss(p, tgt, ww)
+        l.backward()
+        assert abs(float(l) - float(g[name])) < 1e-6
+        gr = p.grad.clone()
+        gr[torch.isinf(pred)] = 0
+        assert np.abs(gr.cpu().numpy() - g[name + "_grad"]).max() < 1e-7
+
+
+def test_standalone_image_losses_match_literal_pytorch(cuda_device):
+    """depth_l1_loss / color_l1_loss / semantic_2d_ce_loss on rendered images against the literal expressions + autograd."""
+    from oracle import losses_ref as R
+    from spsg_b200 import synthetic as S
+    from spsg_b200 import losses as L
+    w, h = 160, 128
+    rc, pred, view, intr, images_depth, images_color, wc, label, cw = _setup(cuda_device, 2, 1, w, h, weight_color=True)
+    with torch.no_grad():
+        imgs = [t.clone() for t in rc(pred["locs"], pred["sdf"], pred["color"], pred["normal"], pred["semantic"], view, intr)]
+    hit = imgs[1] != -float("inf")
+    cases = (
+        ("depth", lambda x: R.depth_l1_loss(x, images_depth, S.VOXELSIZE), lambda x: L.depth_l1_loss(x, images_depth, S.VOXELSIZE), imgs[1], hit),
+        ("colour", lambda x: R.compute_2dcolor_loss(x, images_color, wc), lambda x: L.color_l1_loss(x, images_color, wc), imgs[0], hit[..., None].expand_as(imgs[0])),
+        ("colour/no weight", lambda x: R.compute_2dcolor_loss(x, images_color, None), lambda x: L.color_l1_loss(x, images_color), imgs[0], hit[..., None].expand_as(imgs[0])),
+        ("semantic", lambda x: R.semantic_2d_ce_loss(x, label, cw), lambda x: L.semantic_2d_ce_loss(x, label, cw), imgs[3], hit[..., None].expand_as(imgs[3])),
+    )
+    for name, ref_fn, our_fn, image, valid in cases:
+        a = image.clone().requires_grad_(True)
+        la = ref_fn(a)
+        la.backward()
+        b = image.clone().requires_grad_(True)
+        lb = our_fn(b)
+        (lb * 1.5).backward()
+        torch.testing.assert_close(lb.detach(), la.detach(), rtol=1e-5, atol=1e-7)
+        ga, gb = a.grad[valid] * 1.5, b.grad[valid]
+        scale = float(ga.abs().max())
+        assert scale > 0, name
+        assert float((ga - gb).abs().max()) <= 1e-4 * scale, name
+        assert bool((b.grad[~valid] == 0).all()), name

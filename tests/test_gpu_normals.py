@@ -101,3 +101,19 @@ def test_normals_argument_errors(cuda_device):
         compute_normals_sparse(torch.zeros(1, 4, dtype=torch.long), torch.zeros(1, 1), (4, 4, 4))
     out = compute_normals_sparse(torch.zeros(0, 4, dtype=torch.long, device=cuda_device), torch.zeros(0, 1, device=cuda_device), (4, 4, 4))
     assert out.shape == (0, 3)
+
+
+def test_normals_match_reference_python_golden(cuda_device):
+    """Against outputs of the reference's own loss.compute_normals_sparse (tests/golden/losses_ref.npz)."""
+    import os
+    from spsg_b200.normals import compute_normals_sparse
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "losses_ref.npz"))
+    locs = torch.from_numpy(g["n_locs"]).to(cuda_device)
+    dims, w = tuple(int(v) for v in g["n_dims"]), torch.from_numpy(g["n_w"]).to(cuda_device)
+    for name, tr in (("normals_t", torch.from_numpy(g["n_transform"]).to(cuda_device)), ("normals_id", None)):
+        v = torch.from_numpy(g["n_sdf"]).to(cuda_device).requires_grad_(True)
+        n = compute_normals_sparse(locs, v, dims, tr, num_chunks=2)
+        (n * w).sum().backward()
+        assert np.abs(n.detach().cpu().numpy() - g[name]).max() < 1e-5
+        want = g[name + "_dsdf"]
+        assert np.abs(v.grad.cpu().numpy() - want).max() < 1e-4 * np.abs(want).max()

@@ -247,7 +247,7 @@ def test_golden_vectors_bit_exact(cuda_device):
     Needs no reference binary at run time."""
     import glob
     import os
-    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sphere_*.npz")))
     assert files, "golden vectors missing"
     for f in files:
         g = np.load(f)

@@ -148,7 +148,7 @@ def test_golden_vectors_from_reference_extension():
     B200).  The CPU restatement must reproduce them: same hit mask up to eps-ambiguous rays, values to 1e-4."""
     import glob
     import os
-    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sphere_*.npz")))
     if not files:
         pytest.skip("no golden vectors committed yet")
     for f in files:
@@ -171,3 +171,29 @@ def test_golden_vectors_from_reference_extension():
         if (hit_ref != hit).sum() == 0:
             np.testing.assert_allclose(d[1], g["d_depth"], rtol=1e-3, atol=1e-5)
             np.testing.assert_allclose(d[3], g["d_semantic"], rtol=1e-3, atol=1e-5)
+
+
+def test_loss_restatements_match_reference_python_golden():
+    """oracle/losses_ref.py against outputs of the reference's own loss.py (tests/golden/make_golden_losses.py)."""
+    import os
+    import torch
+    from oracle import losses_ref as R
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "losses_ref.npz"))
+    locs, sdf = torch.from_numpy(g["n_locs"]), torch.from_numpy(g["n_sdf"])
+    dims, w = tuple(int(v) for v in g["n_dims"]), torch.from_numpy(g["n_w"])
+    for name, tr in (("normals_t", torch.from_numpy(g["n_transform"])), ("normals_id", None)):
+        v = sdf.clone().requires_grad_(True)
+        n = R.compute_normals_sparse(locs, v, dims, tr)
+        (n * w).sum().backward()
+        assert np.abs(n.detach().numpy() - g[name]).max() < 1e-6
+        assert np.abs(v.grad.numpy() - g[name + "_dsdf"]).max() < 1e-4 * np.abs(g[name + "_dsdf"]).max()
+    pred, tgt = torch.from_numpy(g["c_pred"]), torch.from_numpy(g["c_tgt"])
+    for name, ww in (("color_w", torch.from_numpy(g["c_weight"])), ("color_now", None)):
+        p = pred.clone().requires_grad_(True)
+        l = R.compute_2dcolor_loss(p, tgt, ww)
+        l.backward()
+        assert abs(float(l) - float(g[name])) < 1e-6
+        hole = torch.isinf(pred)
+        gr = p.grad.clone()
+        gr[hole] = 0
+        assert np.abs(gr.numpy() - g[name + "_grad"]).max() < 1e-7
