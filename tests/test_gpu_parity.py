@@ -269,3 +269,34 @@ def test_golden_vectors_bit_exact(cuda_device):
         for got, key in ((col.grad, "d_color"), (sdf.grad, "d_depth"), (nrm.grad, "d_normal"), (sem.grad, "d_semantic")):
             ref = torch.from_numpy(g[key]).to(cuda_device)
             assert bool(((got - ref).abs() <= 1e-3 * ref.abs() + 1e-5).all()), key
+
+
+def test_forward_bit_exact_whole_room_grid(cuda_device):
+    """test_scene.py's use: one whole room (grid far larger than a chunk, so the chunk maps do NOT fit in shared memory
+    and the forward takes its global-memory map path + the separate block-map kernel), 480x384 top-down view
+    (test_scene.py:89-95, 182-187), grid dims not multiples of the 32-voxel super block."""
+    from spsg_b200 import synthetic as S
+    dims = (72, 132, 168)
+    batch, t = scene_tensors([41], cuda_device, dims_zyx=dims)
+    n = t["locs"].shape[0]
+    w, h = 480, 384
+    # camera above the room centre looking down -z, x right, y flipped (test_scene.py:91-95)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 0], pose[:3, 1], pose[:3, 2] = (1, 0, 0), (0, -1, 0), (0, 0, -1)
+    pose[:3, 3] = (dims[2] // 2, dims[1] // 2, dims[0] * 2)
+    view = torch.from_numpy(pose[None]).to(cuda_device)
+    intr = torch.tensor([[269.112, 269.297, w // 2, h // 2]], device=cuda_device)
+    mine = _mine(cuda_device, 1, dims, w, h, n)
+    ref = _ref(cuda_device, 1, dims, w, h, n)
+    sdf = t["sdf"].clone().requires_grad_(True)
+    sem = t["semantic"].clone().requires_grad_(True)
+    out_m = mine(t["locs"], sdf, t["color"], t["normal"], sem, view, intr)
+    out_r = ref.forward(t["locs"], t["sdf"], t["color"], t["normal"], t["semantic"], view, intr)
+    _assert_render_equal(out_m, out_r, "room")
+    assert (out_m[1] != NINF).float().mean().item() > 0.03
+    assert torch.equal(mine.mapping3dto2d_num[:n], ref.mapping3dto2d_num[:n])
+    grads = [torch.randn_like(o) for o in out_m]
+    torch.autograd.backward(out_m, grads)
+    d_ref = ref.backward(*grads)
+    for g, r in ((sdf.grad, d_ref[1]), (sem.grad, d_ref[3])):
+        assert bool(((g - r).abs() <= 1e-3 * r.abs() + 1e-5).all())
