@@ -213,6 +213,37 @@ SPSG_API int spsg_losses2d_backward(const spsg_loss_targets *t, const float *ima
                                     const float *grad_scale, float *d_color, float *d_depth, float *d_semantic,
                                     void *stream);
 
+/* ---- depth-frame utilities: the reference's second extension on the training step, torch/utils/depth_utils
+ *      (depth_utils_cuda.cpp:80-85, depth_utils_cuda_kernel.cu; Python depth_utils.py:46-100).  Images are (B,1,H,W)
+ *      f32 depth in metres (0 = hole), camera space / normals (B,H,W,3), intrinsics (B,4) = fx,fy,mx,my. ---- */
+#define SPSG_DEPTH_MAX_FILL_ROUNDS 64
+
+/* == depth_utils_cuda.bilateral_filter_floatmap (depth_utils_cuda_kernel.cu:41-86, 215-243) */
+SPSG_API int spsg_depth_bilateral_filter(const float *depth, float *filtered, int32_t batch, int32_t height, int32_t width,
+                                         float sigma_d, float sigma_r, void *stream);
+
+/* == depth_utils_cuda.median_fill_depthmap(out, in) (depth_utils_cuda_kernel.cu:89-140, 245-268): 11x11 median fill of
+ *    hole pixels, everything else copied.  Not in place. */
+SPSG_API int spsg_depth_median_fill(const float *in, float *out, int32_t batch, int32_t height, int32_t width, void *stream);
+
+/* == depth_utils_cuda.convert_depth_to_cameraspace (depth_utils_cuda_kernel.cu:142-170, 296-323) */
+SPSG_API int spsg_depth_to_cameraspace(const float *depth, const float *intrinsics, float *camspace, int32_t batch,
+                                       int32_t height, int32_t width, void *stream);
+
+/* == depth_utils_cuda.compute_normals (depth_utils_cuda_kernel.cu:172-211, 270-294): camera space (B,H,W,3) -> normals */
+SPSG_API int spsg_depth_compute_normals(const float *camspace, float *normals, int32_t batch, int32_t height,
+                                        int32_t width, void *stream);
+
+/* == Depth2Normals.forward (depth_utils.py:84-100) enqueued in one go: bilateral filter into `filtered`, up to
+ *    max_fill_iters/2 rounds of { depth <- fill(filtered); filtered <- fill(depth) } that modify `depth` IN PLACE like the
+ *    reference and stop on the device as soon as a round leaves no hole, then camera space (may be NULL) + normals
+ *    (depth_utils_cuda_kernel.cu:172-211) from the filled depth.  hole_counts: SPSG_DEPTH_MAX_FILL_ROUNDS + 1 device
+ *    int32; [0] = holes of the input, [r] = holes left after round r (0 for rounds that did not run).  The caller reads
+ *    hole_counts[max_fill_iters / 2] (one synchronisation) to decide whether the reference would have returned None. */
+SPSG_API int spsg_depth_to_normals(float *depth, const float *intrinsics, float *filtered, float *camspace, float *normals,
+                                   int32_t *hole_counts, int32_t batch, int32_t height, int32_t width, float sigma_d,
+                                   float sigma_r, int32_t max_fill_iters, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,43 @@ def module():
     return _mod
 
 
+_depth_mod = None
+
+
+def depth_available():
+    return os.path.isfile(os.path.join(REF_DIR, "spsg_ref_depth_utils_cuda.so"))
+
+
+def depth_module():
+    """The compiled reference depth_utils extension (oracle/build_ref.py::build_depth)."""
+    global _depth_mod
+    if _depth_mod is None:
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import spsg_ref_depth_utils_cuda
+        _depth_mod = spsg_ref_depth_utils_cuda
+    return _depth_mod
+
+
+def ref_depth2normals(depth, intrinsics, filter_helper, camspace, normals, max_num_fill_iters=40):
+    """Depth2Normals.forward of the reference, statement by statement (depth_utils.py:84-100), on its native entry points."""
+    m = depth_module()
+    m.bilateral_filter_floatmap(filter_helper, depth, 2.0, 0.1)
+    if max_num_fill_iters > 0:
+        invalid = bool((depth == 0).any())
+        for _ in range(max_num_fill_iters // 2):
+            if not invalid:
+                break
+            m.median_fill_depthmap(depth, filter_helper)      # median_fill_depthmap(filt, img, 2), depth_utils.py:55-59
+            m.median_fill_depthmap(filter_helper, depth)
+            invalid = bool((depth == 0).any())
+        if invalid:
+            return None
+    m.convert_depth_to_cameraspace(camspace, depth, intrinsics, 0.0, 0.0)
+    m.compute_normals(normals, camspace)
+    return normals.permute(0, 3, 1, 2).contiguous()
+
+
 class RefRaycaster:
     def __init__(self, batch_size, dims3d, width, height, depth_min, depth_max, thresh, inc, max_locs, max_pix=64,
                  device="cuda"):

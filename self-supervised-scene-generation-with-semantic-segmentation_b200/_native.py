@@ -15,6 +15,7 @@ SPSG_FLAG_NO_BRICK_SKIP = 1 << 1
 SPSG_FLAG_RECORD_HITS = 1 << 2
 SPSG_FLAG_GRADS_CLEARED = 1 << 3
 SPSG_LOSS_OUT_FLOATS = 8
+SPSG_DEPTH_MAX_FILL_ROUNDS = 64
 
 # every symbol include/spsg_raycast.h declares (tests check the library exports them all)
 EXPORTS = (
@@ -22,6 +23,8 @@ EXPORTS = (
     "spsg_raycast_forward_indexed", "spsg_raycast_backward", "spsg_raycast_occ", "spsg_raycast_forward_loss",
     "spsg_raycast_backward_loss", "spsg_timing_enable", "spsg_timing_read", "spsg_normals_forward",
     "spsg_normals_backward", "spsg_losses2d_forward", "spsg_losses2d_backward",
+    "spsg_depth_bilateral_filter", "spsg_depth_median_fill", "spsg_depth_to_cameraspace", "spsg_depth_to_normals",
+    "spsg_depth_compute_normals",
 )
 
 
@@ -93,6 +96,17 @@ def _load():
     lib.spsg_losses2d_forward.argtypes = [lt, vp, vp, vp, i64, vp, vp, sz, vp]
     lib.spsg_losses2d_backward.restype = ctypes.c_int
     lib.spsg_losses2d_backward.argtypes = [lt, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    f32 = ctypes.c_float
+    lib.spsg_depth_bilateral_filter.restype = ctypes.c_int
+    lib.spsg_depth_bilateral_filter.argtypes = [vp, vp, i32, i32, i32, f32, f32, vp]
+    lib.spsg_depth_median_fill.restype = ctypes.c_int
+    lib.spsg_depth_median_fill.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.spsg_depth_to_cameraspace.restype = ctypes.c_int
+    lib.spsg_depth_to_cameraspace.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.spsg_depth_compute_normals.restype = ctypes.c_int
+    lib.spsg_depth_compute_normals.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.spsg_depth_to_normals.restype = ctypes.c_int
+    lib.spsg_depth_to_normals.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
     lib.spsg_timing_enable.restype = None
     lib.spsg_timing_enable.argtypes = [ctypes.c_int]
     lib.spsg_timing_read.restype = ctypes.c_int

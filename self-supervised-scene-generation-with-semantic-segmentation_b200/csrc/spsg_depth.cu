@@ -1,0 +1,260 @@
+// spsg_depth.cu -- sm_100a kernels + C ABI for the depth-frame utilities of the training step: the reference's second
+// CUDA extension, torch/utils/depth_utils (depth_utils_cuda_kernel.cu, cited as dkernel.cu:<line>), which turns the
+// sensor depth frame into target normals and fills its holes in place (Depth2Normals, depth_utils.py:66-100).
+// SURVEY.md section 8(f) rank 3.
+//
+// Same arithmetic as the reference, expression by expression (float / double mix of the two Gaussians included), so that
+// the results can be compared bit for bit with the compiled reference extension.  What changes is the shape of the work:
+//   * depth -> camera space -> normals is one kernel (the camera-space image is still written: callers can read it);
+//   * the median hole fill selects the reference's order statistic by rank counting instead of a 121-element bubble
+//     sort in local memory, and only for hole pixels;
+//   * the fill iterations terminate on the device: every fill pass counts the holes it leaves and the following passes
+//     return at once when that count is zero, so the whole pipeline is enqueued without a host round trip per iteration
+//     (the reference synchronises on `(depth == 0).any()` up to 21 times, depth_utils.py:86-92).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "spsg_internal.h"
+#include "spsg_raycast.h"
+
+namespace {
+
+constexpr int kFillRadius = 5;  // STRUCTURE_SIZE, dkernel.cu:88
+constexpr int kFillDiameter = 2 * kFillRadius + 1;
+constexpr int kFillCells = kFillDiameter * kFillDiameter;
+
+__device__ __forceinline__ bool depth_valid(float d) { return d != -CUDART_INF_F && d != 0.0f; }
+
+// bilateral_filter_floatmap_kernel (dkernel.cu:41-86); also counts the holes of the input (zero pixels) into *holes.
+__global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
+                                                        int height, float sigmaD, float sigmaR, int32_t *holes) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const float *img = in + (size_t)blockIdx.z * width * height;
+    const bool inside = x < width && y < height;
+    float result = 0.0f;
+    bool hole = false;
+    if (inside) {
+        const int radius = (int)ceil(2.0 * sigmaD);  // dkernel.cu:56
+        const float center = img[y * width + x];
+        hole = center == 0.0f;
+        if (depth_valid(center)) {
+            float sum = 0.0f, sum_weight = 0.0f;
+            for (int m = x - radius; m <= x + radius; m++)
+                for (int n = y - radius; n <= y + radius; n++)
+                    if (m >= 0 && n >= 0 && m < width && n < height) {
+                        const float cur = img[n * width + m];
+                        if (depth_valid(cur)) {
+                            const int dx = m - x, dy = n - y;
+                            const float dist = cur - center;
+                            // gaussD in float, gaussR through double, exactly as written at dkernel.cu:16-29
+                            const float gd = exp(-((dx * dx + dy * dy) / (2.0f * sigmaD * sigmaD)));
+                            const float gr = exp(-(dist * dist) / (2.0 * sigmaR * sigmaR));
+                            const float weight = gd * gr;
+                            sum_weight += weight;
+                            sum += weight * cur;
+                        }
+                    }
+            if (sum_weight > 0.0f) result = sum / sum_weight;
+        }
+        out[(size_t)blockIdx.z * width * height + y * width + x] = result;
+    }
+    if (holes) {
+        const unsigned m = __ballot_sync(0xffffffffu, hole);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(holes, __popc(m));
+    }
+}
+
+// median_fill_depthmap_kernel (dkernel.cu:89-140).  Valid pixels are copied.  A hole takes the order statistic the
+// reference reads out of its sorted 11x11 window: the ((n+1)/2)-th smallest (0-based) of the n valid values, each
+// quantised to millimetres as (int)(1000 d + 0.5f).  (For n < 2 the reference indexes past its array; here: 0.)
+// `gate` (may be NULL): the pass does nothing when *gate == 0.  `holes_out` (may be NULL): counts the zeros written.
+__global__ void __launch_bounds__(256) median_fill_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
+                                                          int height, const int32_t *gate, int32_t *holes_out) {
+    if (gate && *gate == 0) return;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const float *img = in + (size_t)blockIdx.z * width * height;
+    bool hole = false;
+    if (x < width && y < height) {
+        const float cur = img[y * width + x];
+        float result = cur;
+        if (!depth_valid(cur)) {
+            int vals[kFillCells];
+            int n = 0;
+            for (int i = -kFillRadius; i <= kFillRadius; i++)
+                for (int j = -kFillRadius; j <= kFillRadius; j++) {
+                    const int xx = x + j, yy = y + i;
+                    if (xx >= 0 && xx < width && yy >= 0 && yy < height) {
+                        const float d = img[yy * width + xx];
+                        if (depth_valid(d)) vals[n++] = (int)(1000 * d + 0.5f);
+                    }
+                }
+            int val = 0;
+            if (n >= 2) {
+                const int k = (n + 1) / 2;  // rank among the valid values, ascending
+                for (int i = 0; i < n; i++) {
+                    const int v = vals[i];
+                    int less = 0, equal = 0;
+                    for (int j = 0; j < n; j++) {
+                        less += vals[j] < v;
+                        equal += vals[j] == v;
+                    }
+                    if (less <= k && k < less + equal) {
+                        val = v;
+                        break;
+                    }
+                }
+            }
+            result = val <= 0 ? 0.0f : 0.001f * (float)val;
+        }
+        out[(size_t)blockIdx.z * width * height + y * width + x] = result;
+        hole = result == 0.0f;
+    }
+    if (holes_out) {
+        const unsigned m = __ballot_sync(0xffffffffu, hole);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(holes_out, __popc(m));
+    }
+}
+
+__device__ __forceinline__ float3 normal_from_points(float3 cc, float3 pc, float3 cp, float3 mc, float3 cm) {
+    float3 out = make_float3(0.0f, 0.0f, 0.0f);
+    const float ninf = -CUDART_INF_F;
+    if ((cc.x != 0 || pc.x != 0 || cp.x != 0 || mc.x != 0 || cm.x != 0) &&
+        (cc.x != ninf && pc.x != ninf && cp.x != ninf && mc.x != ninf && cm.x != ninf)) {
+        const float ax = __fadd_rn(pc.x, -mc.x), ay = __fadd_rn(pc.y, -mc.y), az = __fadd_rn(pc.z, -mc.z);
+        const float bx = __fadd_rn(cp.x, -cm.x), by = __fadd_rn(cp.y, -cm.y), bz = __fadd_rn(cp.z, -cm.z);
+        // cross (cutil_math.h:1318), length (:1189) and n / -l (:904) with the contraction of the reference's sm_100
+        // SASS: first product of each difference fused, second plain; squares summed x, then y, then z
+        const float nx = __fmaf_rn(ay, bz, -__fmul_rn(az, by)), ny = __fmaf_rn(az, bx, -__fmul_rn(ax, bz)),
+                    nz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
+        const float l = __fsqrt_rn(__fmaf_rn(nz, nz, __fmaf_rn(ny, ny, __fmul_rn(nx, nx))));
+        if (l > 0.0f) out = make_float3(__fdiv_rn(nx, -l), __fdiv_rn(ny, -l), __fdiv_rn(nz, -l));
+    }
+    return out;
+}
+
+// kinectDepthToSkeleton (dkernel.cu:35-39) of one pixel; zero depth gives (0,0,0) (:158-168)
+__device__ __forceinline__ float3 camera_point(const float *img, const float4 k, int width, unsigned x, unsigned y) {
+    const float depth = img[y * width + x];
+    if (depth == 0.0f) return make_float3(0.0f, 0.0f, 0.0f);
+    const float px = __fdiv_rn(__fadd_rn((float)x, -k.z), k.x), py = __fdiv_rn(__fadd_rn((float)y, -k.w), k.y);
+    return make_float3(__fmul_rn(depth, px), __fmul_rn(depth, py), depth);
+}
+
+// convert_depth_to_cameraspace_kernel (dkernel.cu:142-170) + compute_normals_kernel (:172-211) in one pass: the four
+// neighbours' camera-space points are recomputed from the depth image instead of read back from the camspace image.
+__global__ void __launch_bounds__(256) camspace_normals_kernel(const float *__restrict__ depth, const float *__restrict__ intr,
+                                                               float *__restrict__ camspace, float *__restrict__ normals,
+                                                               int width, int height) {
+    const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= (unsigned)width || y >= (unsigned)height) return;
+    const int b = blockIdx.z;
+    const float *img = depth + (size_t)b * width * height;
+    const float4 k = *reinterpret_cast<const float4 *>(intr + (size_t)b * 4);  // fx, fy, mx, my
+    const size_t o = ((size_t)b * height * width + (size_t)y * width + x) * 3;
+    const float3 cc = camera_point(img, k, width, x, y);
+    if (camspace) { camspace[o] = cc.x; camspace[o + 1] = cc.y; camspace[o + 2] = cc.z; }
+    if (!normals) return;
+    float3 out = make_float3(0.0f, 0.0f, 0.0f);
+    if (x > 0 && x < (unsigned)width - 1 && y > 0 && y < (unsigned)height - 1) {
+        const float3 pc = camera_point(img, k, width, x, y + 1), cp = camera_point(img, k, width, x + 1, y);
+        const float3 mc = camera_point(img, k, width, x, y - 1), cm = camera_point(img, k, width, x - 1, y);
+        out = normal_from_points(cc, pc, cp, mc, cm);
+    }
+    normals[o] = out.x; normals[o + 1] = out.y; normals[o + 2] = out.z;
+}
+
+// compute_normals_kernel (dkernel.cu:172-211) on a camera-space image given by the caller
+__global__ void __launch_bounds__(256) normals_from_camspace_kernel(const float *__restrict__ cam, float *__restrict__ normals,
+                                                                    int width, int height) {
+    const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= (unsigned)width || y >= (unsigned)height) return;
+    const float *img = cam + (size_t)blockIdx.z * width * height * 3;
+    auto at = [&](unsigned xx, unsigned yy) {
+        const float *p = img + ((size_t)yy * width + xx) * 3;
+        return make_float3(p[0], p[1], p[2]);
+    };
+    float3 out = make_float3(0.0f, 0.0f, 0.0f);
+    if (x > 0 && x < (unsigned)width - 1 && y > 0 && y < (unsigned)height - 1)
+        out = normal_from_points(at(x, y), at(x, y + 1), at(x + 1, y), at(x, y - 1), at(x - 1, y));
+    float *o = normals + ((size_t)blockIdx.z * width * height + (size_t)y * width + x) * 3;
+    o[0] = out.x; o[1] = out.y; o[2] = out.z;
+}
+
+int check_image(const void *a, const void *b, int batch, int height, int width) {
+    if (!a || !b) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "NULL image pointer");
+    if (batch <= 0 || height <= 0 || width <= 0) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "bad image size");
+    return SPSG_OK;
+}
+
+dim3 image_grid(int batch, int height, int width) { return dim3((width + 31) / 32, (height + 7) / 8, batch); }
+
+}  // namespace
+
+extern "C" {
+
+int spsg_depth_bilateral_filter(const float *depth, float *filtered, int32_t batch, int32_t height, int32_t width,
+                                float sigma_d, float sigma_r, void *stream) {
+    if (int rc = check_image(depth, filtered, batch, height, width)) return rc;
+    bilateral_kernel<<<image_grid(batch, height, width), 256, 0, (cudaStream_t)stream>>>(depth, filtered, width, height, sigma_d,
+                                                                                      sigma_r, nullptr);
+    SPSG_CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_depth_median_fill(const float *in, float *out, int32_t batch, int32_t height, int32_t width, void *stream) {
+    if (int rc = check_image(in, out, batch, height, width)) return rc;
+    if (in == out) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "median fill cannot run in place");
+    median_fill_kernel<<<image_grid(batch, height, width), 256, 0, (cudaStream_t)stream>>>(in, out, width, height, nullptr, nullptr);
+    SPSG_CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_depth_to_cameraspace(const float *depth, const float *intrinsics, float *camspace, int32_t batch, int32_t height,
+                              int32_t width, void *stream) {
+    if (int rc = check_image(depth, camspace, batch, height, width)) return rc;
+    if (!intrinsics || (reinterpret_cast<uintptr_t>(intrinsics) & 15u)) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "intrinsics must be non-NULL and 16-byte aligned");
+    camspace_normals_kernel<<<image_grid(batch, height, width), 256, 0, (cudaStream_t)stream>>>(depth, intrinsics, camspace,
+                                                                                             nullptr, width, height);
+    SPSG_CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_depth_compute_normals(const float *camspace, float *normals, int32_t batch, int32_t height, int32_t width,
+                               void *stream) {
+    if (int rc = check_image(camspace, normals, batch, height, width)) return rc;
+    normals_from_camspace_kernel<<<image_grid(batch, height, width), 256, 0, (cudaStream_t)stream>>>(camspace, normals, width, height);
+    SPSG_CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+int spsg_depth_to_normals(float *depth, const float *intrinsics, float *filtered, float *camspace, float *normals,
+                          int32_t *hole_counts, int32_t batch, int32_t height, int32_t width, float sigma_d, float sigma_r,
+                          int32_t max_fill_iters, void *stream) {
+    if (int rc = check_image(depth, filtered, batch, height, width)) return rc;
+    if (!normals || !hole_counts) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "NULL output pointer");
+    if (!intrinsics || (reinterpret_cast<uintptr_t>(intrinsics) & 15u)) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "intrinsics must be non-NULL and 16-byte aligned");
+    if (max_fill_iters < 0 || max_fill_iters > 2 * (SPSG_DEPTH_MAX_FILL_ROUNDS)) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "max_fill_iters out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = image_grid(batch, height, width);
+    const int rounds = max_fill_iters / 2;  // depth_utils.py:88
+    // hole_counts[0] = zeros of the input frame, hole_counts[r] = zeros left in `depth` after fill round r
+    SPSG_CUDA_TRY(cudaMemsetAsync(hole_counts, 0, sizeof(int32_t) * (SPSG_DEPTH_MAX_FILL_ROUNDS + 1), st));
+    bilateral_kernel<<<grid, 256, 0, st>>>(depth, filtered, width, height, sigma_d, sigma_r, hole_counts);  // depth_utils.py:85
+    SPSG_CUDA_TRY(cudaGetLastError());
+    for (int r = 0; r < rounds; r++) {
+        // one call of median_fill_depthmap(filt, depth, 2) (depth_utils.py:55-59,90): depth <- fill(filtered), filtered <- fill(depth);
+        // both passes return immediately once the previous round left no hole
+        median_fill_kernel<<<grid, 256, 0, st>>>(filtered, depth, width, height, hole_counts + r, hole_counts + r + 1);
+        median_fill_kernel<<<grid, 256, 0, st>>>(depth, filtered, width, height, hole_counts + r, nullptr);
+        SPSG_CUDA_TRY(cudaGetLastError());
+    }
+    camspace_normals_kernel<<<grid, 256, 0, st>>>(depth, intrinsics, camspace, normals, width, height);  // :94-95
+    SPSG_CUDA_TRY(cudaGetLastError());
+    return SPSG_OK;
+}
+
+}  // extern "C"

@@ -56,3 +56,19 @@ def one():
     c = color.clone().requires_grad_(True); d = depth.clone().requires_grad_(True); s = sem.clone().requires_grad_(True)
     L.losses_2d(c, d, s, images_depth=tdepth, images_color=tcolor, target2d_label=label, weight_semantic_class=cw, voxelsize=S.VOXELSIZE)[0].backward()
 print("  same three terms in one pass (losses_2d): %.0f us" % timeit(one))
+
+# ---- Depth2Normals: reference extension pipeline (host check per fill round) vs one enqueued native call
+from oracle import ref_driver
+from spsg_b200.depth_utils import Depth2Normals
+if ref_driver.depth_available():
+    Bd, Hd, Wd = 8, S.HEIGHT, S.WIDTH
+    g2 = torch.Generator().manual_seed(0)
+    base = 1.5 + 0.3 * torch.rand(Bd, 1, Hd, Wd, generator=g2)
+    base[torch.rand(Bd, 1, Hd, Wd, generator=g2) < 0.03] = 0.0
+    base = base.to(dev)
+    intr8 = torch.tensor([list(S.INTRINSICS)] * Bd, device=dev)
+    mod = Depth2Normals(Bd, Wd, Hd, S.DEPTH_MIN, S.DEPTH_MAX, device=dev)
+    filt, cam, nrm = torch.zeros_like(base), torch.zeros(Bd, Hd, Wd, 3, device=dev), torch.zeros(Bd, Hd, Wd, 3, device=dev)
+    print("Depth2Normals, %d frames %dx%d with 3%% holes: reference extension %.0f us, fused pipeline %.0f us" % (
+        Bd, Wd, Hd, timeit(lambda: ref_driver.ref_depth2normals(base.clone(), intr8, filt, cam, nrm)),
+        timeit(lambda: mod(base.clone(), intr8))))
