@@ -716,9 +716,11 @@ constexpr int kTilePix = kTileW * kTileH;
 
 constexpr int kWarpW = 8, kWarpH = 4;                   // pixels per warp tile
 constexpr int kFwdWarps = 24;                           // warps of the persistent forward CTA (one CTA per SM)
+constexpr int kFwdWarpsLarge = 28;                      // ... for launches with many tiles per SM (more latency hiding, a few spills)
 constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
-constexpr size_t kFwdSmemFixed = 128 + (size_t)kFwdWarps * kStageFloats * sizeof(float);
+__host__ __device__ constexpr size_t fwd_smem_fixed(int warps) { return 128 + (size_t)warps * kStageFloats * sizeof(float); }
+constexpr size_t kFwdSmemFixed = fwd_smem_fixed(kFwdWarpsLarge);  // residency test uses the larger CTA
 constexpr size_t kFwdSmemMax = 232448 - 1024;           // 227 KB opt-in limit per CTA, minus the static shared memory
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -782,14 +784,14 @@ __device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, flo
 // CTA i works on chunk i % B (then i % B + gridDim, ...): the chunk's cell-class bit planes and block map are pulled
 // into shared memory once by TMA bulk copies, so the march's "does this sample need arithmetic" lookups never leave
 // the SM; tiles of the chunk's images are dealt to warps first statically, then from a global counter.
-template <bool kLoss, bool kSmemMaps>
-__global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const ForwardArgs a) {
+template <bool kLoss, bool kSmemMaps, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const ForwardArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float4 s_steps[kStepEntries];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *stage = reinterpret_cast<float *>(smem + 128) + warp * kStageFloats;
-    uint2 *s_vbits = reinterpret_cast<uint2 *>(smem + kFwdSmemFixed);
+    uint2 *s_vbits = reinterpret_cast<uint2 *>(smem + fwd_smem_fixed(kWarps));
     uint8_t *s_bmap = reinterpret_cast<uint8_t *>(s_vbits + a.vpc);
     uint8_t *s_tmp = s_bmap + a.bpc;
     const unsigned kFull = 0xffffffffu;
@@ -835,7 +837,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) raycast_forward_kernel(const F
         // CTAs that share this chunk: ranks 0..group-1.  First round static and contiguous per CTA, then dynamic.
         const int nb = a.num_chunks;
         const int group = ((int)gridDim.x - 1 - (int)(blockIdx.x % nb)) / nb + 1, rank = blockIdx.x / nb;
-        const int static_tiles = min(total_tiles, group * kFwdWarps);
+        const int static_tiles = min(total_tiles, group * kWarps);
         const int per = static_tiles / group, extra = static_tiles - per * group;
         const int my_first = rank * per + min(rank, extra), my_count = per + (rank < extra ? 1 : 0);
         int tile = warp < my_count ? my_first + warp : total_tiles;
@@ -1946,7 +1948,10 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     const long long tiles_x = (p->width + kWarpW - 1) / kWarpW, tiles_y = (p->height + kWarpH - 1) / kWarpH;
     const long long all_tiles = ((tiles_x + 1) / 2) * ((tiles_y + 1) / 2) * 4 * p->views_per_chunk * p->num_chunks;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(sms, all_tiles));
-    const size_t dyn = kFwdSmemFixed + (a.maps_in_smem ? map_bytes : 0);
+    // CTA size: 24 warps when every warp gets about one tile (latency-bound), 28 when there are many tiles per SM
+    const bool large = all_tiles >= (long long)sms * 4 * kFwdWarpsLarge;
+    const int warps = large ? kFwdWarpsLarge : kFwdWarps;
+    const size_t dyn = fwd_smem_fixed(warps) + (a.maps_in_smem ? map_bytes : 0);
     {
         static std::mutex mu;
         static bool configured[64] = {false};
@@ -1954,22 +1959,28 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         CUDA_TRY(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lk(mu);
         if (dev < 0 || dev >= 64 || !configured[dev]) {
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
-            CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax));
+#define SPSG_SET_SMEM(L, M, W) CUDA_TRY(cudaFuncSetAttribute(raycast_forward_kernel<L, M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemMax))
+            SPSG_SET_SMEM(true, true, kFwdWarps); SPSG_SET_SMEM(false, true, kFwdWarps);
+            SPSG_SET_SMEM(true, false, kFwdWarps); SPSG_SET_SMEM(false, false, kFwdWarps);
+            SPSG_SET_SMEM(true, true, kFwdWarpsLarge); SPSG_SET_SMEM(false, true, kFwdWarpsLarge);
+            SPSG_SET_SMEM(true, false, kFwdWarpsLarge); SPSG_SET_SMEM(false, false, kFwdWarpsLarge);
+#undef SPSG_SET_SMEM
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
     {
         ScopedKernelTimer timer(0, st);
+#define SPSG_LAUNCH(L, M)                                                                                         \
+    do {                                                                                                          \
+        if (large) raycast_forward_kernel<L, M, kFwdWarpsLarge><<<grid, kFwdWarpsLarge * 32, dyn, st>>>(a);      \
+        else raycast_forward_kernel<L, M, kFwdWarps><<<grid, kFwdWarps * 32, dyn, st>>>(a);                      \
+    } while (0)
         if (targets) {
-            if (a.maps_in_smem) raycast_forward_kernel<true, true><<<grid, kFwdThreads, dyn, st>>>(a);
-            else raycast_forward_kernel<true, false><<<grid, kFwdThreads, dyn, st>>>(a);
+            if (a.maps_in_smem) SPSG_LAUNCH(true, true); else SPSG_LAUNCH(true, false);
         } else {
-            if (a.maps_in_smem) raycast_forward_kernel<false, true><<<grid, kFwdThreads, dyn, st>>>(a);
-            else raycast_forward_kernel<false, false><<<grid, kFwdThreads, dyn, st>>>(a);
+            if (a.maps_in_smem) SPSG_LAUNCH(false, true); else SPSG_LAUNCH(false, false);
         }
+#undef SPSG_LAUNCH
     }
     CUDA_TRY(cudaGetLastError());
     if (targets) {
