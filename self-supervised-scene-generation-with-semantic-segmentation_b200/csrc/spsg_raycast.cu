@@ -662,6 +662,7 @@ __device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restric
 #ifdef SPSG_STATS
 // development build only (-DSPSG_STATS): event counters of the march, read back with spsg_debug_stats()
 __device__ unsigned long long g_stats[48];
+__device__ int g_tile_stats[8192][8];  // per tile: total, setup, march, refine, epilogue cycles, iterations, smid, start
 #define STAT_MAX(k, v) atomicMax(&g_stats[k], (unsigned long long)(v))
 #define STAT_ADD(k, v) atomicAdd(&g_stats[k], (unsigned long long)(v))
 #if SPSG_STATS == 1
@@ -1268,6 +1269,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                     STAT_ADD(44, clk3 - clk_e2); STAT_MAX(45, clk3 - clk_e2);    // staging + stores
                     STAT_ADD(24, clk3 - clk0); STAT_MAX(25, clk3 - clk0);        // whole tile
                     STAT_MAX(26, my_iters);
+                    if (tile < 8192) {
+                        unsigned smid;
+                        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+                        int *ts = g_tile_stats[tile];
+                        ts[0] = (int)(clk3 - clk0); ts[1] = (int)(clk1 - clk0); ts[2] = (int)clk_march; ts[3] = (int)clk_refine;
+                        ts[4] = (int)(clk3 - clk2); ts[5] = my_iters; ts[6] = (int)smid; ts[7] = (int)(clk0 & 0x7fffffff);
+                    }
                     STAT_ADD(27, my_iters);
                     int bucket = 0;
                     for (int t = my_iters; t > 8; t >>= 1) bucket++;
@@ -2072,6 +2080,10 @@ int spsg_internal_fail_cuda(cudaError_t e, const char *where) { return fail_cuda
 extern "C" {
 
 #ifdef SPSG_STATS
+SPSG_API int spsg_debug_tile_stats(int *out) {
+    return cudaMemcpyFromSymbol(out, g_tile_stats, sizeof(int) * 8192 * 8) == cudaSuccess ? SPSG_OK : SPSG_ERR_CUDA;
+}
+
 SPSG_API int spsg_debug_stats(unsigned long long *out, int reset) {
     if (cudaMemcpyFromSymbol(out, g_stats, sizeof(unsigned long long) * 48) != cudaSuccess) return SPSG_ERR_CUDA;
     if (reset) {
