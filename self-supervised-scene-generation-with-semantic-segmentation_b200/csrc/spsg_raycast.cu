@@ -564,8 +564,7 @@ __global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restric
 
 // The same block map, built in place by a whole CTA in shared memory (forward prologue, when the chunk's maps are
 // shared-memory resident): `bm` holds the blocks' region bits (nblocks bytes, as the classifier wrote them) and
-// receives the map; region bits are OR-ed level by level, no atomics.  `tmp` needs n8 + n16 + n32 bytes.  Every
-// thread of the CTA must call it; it starts and ends with a __syncthreads().
+// receives the map.  Every thread of the CTA must call it; it starts and ends with a __syncthreads().
 __host__ __device__ constexpr uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
     const int r[5] = {0, r1, r2, r3, r4};
     int lu = 0, le = 0;
@@ -595,34 +594,52 @@ __device__ __forceinline__ void decode3(int i, int nx, int ny, float inv_nx, flo
     y = q - z * ny;
 }
 
-__device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restrict__ tmp, int nbx, int nby, int nbz) {
+__device__ __forceinline__ void smem_or_byte(uint8_t *p, int bits) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(p);
+    atomicOr(reinterpret_cast<unsigned *>(u & ~(uintptr_t)3), (unsigned)bits << (8 * (int)(u & 3)));
+}
+
+// `tmp` (n8 + n16 + n32 bytes, rounded up to 16) must have been cleared by the CTA before the call.
+__device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restrict__ tmp, const uint8_t *__restrict__ lut,
+                                    int nbx, int nby, int nbz) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int nblocks = nbx * nby * nbz;
     const int ax = (nbx + 1) >> 1, ay = (nby + 1) >> 1, az = (nbz + 1) >> 1;  // 8^3 regions
     const int cx = (ax + 1) >> 1, cy = (ay + 1) >> 1, cz = (az + 1) >> 1;  // 16^3
-    const int ex = (cx + 1) >> 1, ey = (cy + 1) >> 1, ez = (cz + 1) >> 1;  // 32^3
+    const int ex = (cx + 1) >> 1, ey = (cy + 1) >> 1;                      // 32^3
     uint8_t *a8 = tmp, *a16 = a8 + ax * ay * az, *a32 = a16 + cx * cy * cz;
     __syncthreads();
-    // each level: OR of the (up to) 2x2x2 children
-    auto reduce = [&](const uint8_t *src, int sx, int sy, int sz, uint8_t *dst, int dx, int dy, int dz) {
-        const float inv_dx = 1.0f / (float)dx, inv_dy = 1.0f / (float)dy;
-        for (int j = tid; j < dx * dy * dz; j += T) {
-            int x, y, z;
-            decode3(j, dx, dy, inv_dx, inv_dy, x, y, z);
-            int bits = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int xx = 2 * x + (k & 1), yy = 2 * y + ((k >> 1) & 1), zz = 2 * z + (k >> 2);
-                if (xx < sx && yy < sy && zz < sz) bits |= src[(zz * sy + yy) * sx + xx];
-            }
-            dst[j] = (uint8_t)bits;
+    // one pass: every block ORs its region bits into the 8^3 / 16^3 / 32^3 regions around it (shared-memory atomics; most
+    // blocks are empty and contribute nothing)
+    if ((nbx & 3) == 0) {
+        const int wx = nbx >> 2;
+        const float inv_wx = 1.0f / (float)wx, inv_ny = 1.0f / (float)nby;
+        const uint32_t *bm32 = reinterpret_cast<const uint32_t *>(bm);
+        for (int i = tid; i < wx * nby * nbz; i += T) {
+            const uint32_t w = bm32[i];
+            if (w == 0u) continue;
+            int xw, y, z;
+            decode3(i, wx, nby, inv_wx, inv_ny, xw, y, z);
+            const int lo = (int)((w | (w >> 8)) & 7u), hi = (int)(((w >> 16) | (w >> 24)) & 7u);
+            uint8_t *p8 = a8 + ((z >> 1) * ay + (y >> 1)) * ax + 2 * xw;
+            if (lo) smem_or_byte(p8, lo);
+            if (hi) smem_or_byte(p8 + 1, hi);
+            smem_or_byte(a16 + ((z >> 2) * cy + (y >> 2)) * cx + xw, lo | hi);
+            smem_or_byte(a32 + ((z >> 3) * ey + (y >> 3)) * ex + (xw >> 1), lo | hi);
         }
-        __syncthreads();
-    };
-    reduce(bm, nbx, nby, nbz, a8, ax, ay, az);
-    reduce(a8, ax, ay, az, a16, cx, cy, cz);
-    reduce(a16, cx, cy, cz, a32, ex, ey, ez);
-    const uint8_t *__restrict__ lut = kBlockLut.v;
+    } else {
+        const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
+        for (int i = tid; i < nblocks; i += T) {
+            const int bits = bm[i] & 7;
+            if (bits == 0) continue;
+            int x, y, z;
+            decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
+            smem_or_byte(a8 + ((z >> 1) * ay + (y >> 1)) * ax + (x >> 1), bits);
+            smem_or_byte(a16 + ((z >> 2) * cy + (y >> 2)) * cx + (x >> 2), bits);
+            smem_or_byte(a32 + ((z >> 3) * ey + (y >> 3)) * ex + (x >> 3), bits);
+        }
+    }
+    __syncthreads();
     if ((nbx & 3) == 0) {
         // four blocks of an x row per 32-bit word: they share their 16^3 / 32^3 regions and two 8^3 regions
         const int wx = nbx >> 2;
@@ -639,7 +656,7 @@ __device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restric
             uint32_t out = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                out |= (uint32_t)__ldg(lut + (((w >> (8 * k)) & 7u) | (unsigned)(k < 2 ? lo0 : lo1) | (unsigned)hi)) << (8 * k);
+                out |= (uint32_t)lut[((w >> (8 * k)) & 7u) | (unsigned)(k < 2 ? lo0 : lo1) | (unsigned)hi] << (8 * k);
             bm32[i] = out;
         }
     } else {
@@ -647,9 +664,9 @@ __device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restric
         for (int i = tid; i < nblocks; i += T) {
             int x, y, z;
             decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
-            bm[i] = __ldg(lut + ((bm[i] & 7) | ((int)a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)] << 3) |
-                                 ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)] << 6) |
-                                 ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)] << 9)));
+            bm[i] = lut[(bm[i] & 7) | ((int)a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)] << 3) |
+                        ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)] << 6) |
+                        ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)] << 9)];
         }
     }
     __syncthreads();
@@ -693,7 +710,7 @@ struct ForwardArgs {
     const uint2 *vbits;   // [B][vpc]
     const uint8_t *bmap;  // [B][bpc]
     const uint8_t *marks; // [B][bpc] region bits of the 4^3 blocks
-    size_t vpc, bpc;
+    size_t vpc, bpc, tmp_bytes;
     int wpr;
     int maps_in_smem;
     int32_t *tile_counter;  // [B], zeroed per call
@@ -722,7 +739,7 @@ constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
 __host__ __device__ constexpr size_t fwd_smem_fixed(int warps) { return 128 + (size_t)warps * kStageFloats * sizeof(float); }
 constexpr size_t kFwdSmemFixed = fwd_smem_fixed(kFwdWarpsLarge);  // residency test uses the larger CTA
-constexpr size_t kFwdSmemMax = 232448 - 1024;           // 227 KB opt-in limit per CTA, minus the static shared memory
+constexpr size_t kFwdSmemMax = 232448 - 5120;           // 227 KB opt-in limit per CTA, minus the static shared memory
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -789,6 +806,7 @@ template <bool kLoss, bool kSmemMaps, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const ForwardArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float4 s_steps[kStepEntries];
+    __shared__ __align__(16) uint8_t s_lut[kSmemMaps ? 4096 : 16];  // block_map_byte as a table (block-map build)
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *stage = reinterpret_cast<float *>(smem + 128) + warp * kStageFloats;
@@ -799,6 +817,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
     const float kInf = CUDART_INF_F;
 
     if (threadIdx.x < kStepEntries) step_table_fill(s_steps, threadIdx.x, a.inc);
+    if (kSmemMaps)
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(kBlockLut.v) + i);
     if (kSmemMaps && threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     unsigned phase = 0;
@@ -939,9 +960,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
         TileRay q;
         q.inside = false;
         if (tile < total_tiles) prepare(tile, q);
+#ifdef SPSG_STATS
+        const long long clk_p0 = clock64();
+#endif
         if (kSmemMaps) {
+            for (int i = threadIdx.x; i < (int)(a.tmp_bytes >> 2); i += blockDim.x) reinterpret_cast<uint32_t *>(s_tmp)[i] = 0u;
             mbar_wait(mbar, phase);  // the chunk's class planes and region bits have landed
-            build_block_map_cta(s_bmap, s_tmp, a.nbx, a.nby, a.nbz);
+#ifdef SPSG_STATS
+            const long long clk_p1 = clock64();
+            if (lane == 0) { STAT_ADD(4, clk_p1 - clk_p0); STAT_MAX(5, clk_p1 - clk_p0); }
+#endif
+            build_block_map_cta(s_bmap, s_tmp, s_lut, a.nbx, a.nby, a.nbz);
+#ifdef SPSG_STATS
+            if (lane == 0) { STAT_ADD(6, clock64() - clk_p1); STAT_MAX(7, clock64() - clk_p1); STAT_ADD(13, 1); }
+#endif
         }
 
         while (tile < total_tiles) {
@@ -1931,7 +1963,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
     a.dense = dense; a.vbits = vbits; a.bmap = bmap; a.vpc = L.vpc; a.bpc = L.bpc; a.wpr = L.wpr;
-    a.marks = marks;
+    a.marks = marks; a.tmp_bytes = tmp_bytes;
     a.tile_counter = (int32_t *)(ws + L.tiles_off);
     a.num_chunks = p->num_chunks;
     a.list_count = (int32_t *)(ws + L.head_off);

@@ -29,6 +29,8 @@ for B, F in ((1, 1), (8, 5)):
             print("  %-14s %12d  per ray %.2f  per warp %.2f" % (nm, out[k], out[k] / rays, out[k] / warps))
     for k, nm in ((16, "setup+clip"), (28, "wait maps"), (18, "march"), (20, "refine"), (22, "epilogue"), (40, "  payload+atom"), (42, "  list append"), (44, "  stage+store"), (24, "whole")):
         print("  cycles %-10s avg/warp %8.0f  max %8d" % (nm, out[k] / warps, out[k + 1]))
+    if out[13]:
+        print("  per warp: wait for TMA after prepare avg %.0f max %d; block-map build (incl. its barriers) avg %.0f max %d" % (out[4] / out[13], out[5], out[6] / out[13], out[7]))
     print("  warp iterations avg %.1f max" % (out[27] / warps), out[26], " histogram (<=8,16,32,...):", [out[32 + i] for i in range(10)])
     cnt = m.mapping3dto2d_num[:n * F]
     hist = torch.bincount(cnt.clamp(max=64))
