@@ -101,6 +101,7 @@ struct Layout {
     size_t zero_off, zero_bytes;    // everything from here to the list is cleared by the fill kernel of every forward
     size_t head_off;                // int32 list counter (256 B)
     size_t tiles_off, tiles_bytes;  // int32 [B] dynamic tile counters of the forward
+    size_t arrive_off, arrive_bytes;  // int32 [B][super blocks]: classifier warps done per 32^3 super block
     size_t loss_off, loss_bytes;    // double[kLossSlots][8] loss accumulators
     size_t list_off, list_bytes;    // int2 (voxel, image) per (voxel, view) pair that received a pixel
     size_t hits_off, hits_bytes;    // optional int32 per-pixel hit voxel
@@ -136,6 +137,9 @@ Layout make_layout(const spsg_raycast_params *p) {
     L.tiles_off = off;
     L.tiles_bytes = align_up((size_t)p->num_chunks * sizeof(int32_t), 256);
     off += L.tiles_bytes;
+    L.arrive_off = off;
+    L.arrive_bytes = align_up((size_t)p->num_chunks * ((L.nbz + 7) / 8) * ((L.nby + 7) / 8) * L.wpr * sizeof(int32_t), 256);
+    off += L.arrive_bytes;
     L.loss_off = off;
     L.loss_bytes = align_up((size_t)kLossSlots * 8 * sizeof(double), 256);
     off += L.loss_bytes;
@@ -435,6 +439,33 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
         for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
 }
 
+// Block map.  bits of a region = OR over its cells of {1: positive cell, 2: negative cell, 4: mixed cell}.  A region
+// is sign-uniform when it has no mixed cell and not both signs; empty when it has no valid cell at all.  Every 4^3
+// block gets the largest aligned region (edge 4, 8, 16, 32 = level 1..4) around it that is uniform:
+//   empty     if that region is empty, or no larger than the largest empty region around the block (one jump);
+//   positive / negative otherwise (two events: jump to the region's last sample, then step out);
+//   surface   (byte 0) if even the block itself is not uniform: samples there are classified cell by cell.
+__host__ __device__ constexpr uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
+    const int r[5] = {0, r1, r2, r3, r4};
+    int lu = 0, le = 0;
+    for (int l = 1; l <= 4; l++) {
+        if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
+        if (r[l] == 0) le = l;
+    }
+    if (lu == 0) return 0;
+    const int kind = (le == lu) ? kKindEmpty : (r[lu] & 1) ? kKindPos : kKindNeg;
+    return (uint8_t)((kind << 3) | lu);
+}
+
+// the same function as a table over the four 3-bit region words (r1 | r2 << 3 | r3 << 6 | r4 << 9)
+struct BlockLut { uint8_t v[4096]; };
+constexpr BlockLut make_block_lut() {
+    BlockLut t{};
+    for (int i = 0; i < 4096; i++) t.v[i] = block_map_byte(i & 7, (i >> 3) & 7, (i >> 6) & 7, (i >> 9) & 7);
+    return t;
+}
+__device__ const BlockLut kBlockLut = make_block_lut();
+
 // Cell classes.  For the cell c = (x, y, z) look at the 8 voxels (x..x+1, y..y+1, z..z+1), the corners of every
 // sample whose corner (0,0,0) is c (kernel.cu:131-153):
 //   invalid  some corner absent or outside the grid: such a sample is invalid;
@@ -451,7 +482,8 @@ constexpr float kTiny = 1e-30f, kHuge = 3e38f;
 __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict__ dense, uint2 *__restrict__ vbits,
                                                          size_t vpc, uint8_t *__restrict__ marks,
                                                          int dimz, int dimy, int dimx, int wpr, int nby, int nbx,
-                                                         size_t bpc) {
+                                                         size_t bpc, uint8_t *__restrict__ bmap, int32_t *__restrict__ arrive,
+                                                         int nbz) {
     const unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5);  // (block row in y, xw) of this warp's slab
@@ -509,167 +541,63 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
                 (uint8_t)((((any_pos >> (4 * lane)) & 0xfu) ? 1 : 0) | (((any_neg >> (4 * lane)) & 0xfu) ? 2 : 0) |
                           (((any_mix >> (4 * lane)) & 0xfu) ? 4 : 0));
     }
-}
-
-// Block map.  bits of a region = OR over its cells of {1: positive cell, 2: negative cell, 4: mixed cell}.  A region
-// is sign-uniform when it has no mixed cell and not both signs; empty when it has no valid cell at all.  Every 4^3
-// block gets the largest aligned region (edge 4, 8, 16, 32 = level 1..4) around it that is uniform:
-//   empty     if that region is empty, or no larger than the largest empty region around the block (one jump);
-//   positive / negative otherwise (two events: jump to the region's last sample, then step out);
-//   surface   (byte 0) if even the block itself is not uniform: samples there are classified cell by cell.
-// One CTA per 32^3-voxel super block (8^3 blocks).
-__global__ void __launch_bounds__(512) block_map_kernel(const uint8_t *__restrict__ marks,
-                                                        uint8_t *__restrict__ bmap, size_t bpc, int nbz, int nby,
-                                                        int nbx, int sbz, int sby, int sbx) {
-    __shared__ int agg8[64], agg16[8], agg32;
-    const int t = threadIdx.x;
-    if (t < 64) agg8[t] = 0;
-    if (t < 8) agg16[t] = 0;
-    if (t == 0) agg32 = 0;
-    __syncthreads();
-    int sb = blockIdx.x;
-    const int bx = sb % sbx; sb /= sbx;
-    const int by = sb % sby; sb /= sby;
-    const int bz = sb % sbz;
-    const int chunk = sb / sbz;
-    const int tx = t & 7, ty = (t >> 3) & 7, tz = t >> 6;
-    const int fx = bx * kSuper + tx, fy = by * kSuper + ty, fz = bz * kSuper + tz;
-    const bool inside = fx < nbx && fy < nby && fz < nbz;
-    const size_t at = (size_t)chunk * bpc + ((size_t)fz * nby + fy) * nbx + fx;
-    int bits = 0;
-    if (inside) bits = marks[at];
-    const int i8 = (tz >> 1) * 16 + (ty >> 1) * 4 + (tx >> 1), i16 = (tz >> 2) * 4 + (ty >> 2) * 2 + (tx >> 2);
-    if (bits) {
-        atomicOr(&agg8[i8], bits);
-        atomicOr(&agg16[i16], bits);
-        atomicOr(&agg32, bits);
-    }
-    __syncthreads();
-    if (inside) {
-        const int r[5] = {0, bits, agg8[i8], agg16[i16], agg32};
-        int lu = 0, le = 0;  // largest uniform / largest empty level (regions nest, so the predicates are monotone)
+    // ---- block map of the 32^3 super block (8 x 8 slabs of this x word) by whichever of its warps finishes last
+    const int sby = (nby + 7) >> 3, sbz = (nbz + 7) >> 3;
+    const int sy = yb >> 3, sz = zb >> 3;
+    const int rows_y = min(8, nby - sy * 8), rows_z = min(8, nbz - sz * 8);
+    __threadfence();  // this warp's region bits are visible before it is counted
+    int prev = 0;
+    if (lane == 0) prev = atomicAdd(arrive + ((size_t)chunk * sbz + sz) * sby * wpr + (size_t)sy * wpr + xw, 1);
+    prev = __shfl_sync(kFull, prev, 0);
+    if (prev != rows_y * rows_z - 1) return;
+    __threadfence();
+    // lane = zl * 4 + (yl >> 1) owns the two slab rows (zl, yl), (zl, yl + 1), yl even: eight region bytes each
+    const int zl = lane >> 2, yl = (lane & 3) * 2;
+    uint32_t rb[2][2] = {{0u, 0u}, {0u, 0u}};  // [row][x half]: four blocks per word
+    const int nx = min(8, nbx - xw * 8);
 #pragma unroll
-        for (int l = 1; l <= 4; l++) {
-            if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
-            if (r[l] == 0) le = l;
-        }
-        uint8_t byte = 0;
-        if (lu > 0) {
-            const int kind = (le == lu) ? kKindEmpty : (r[lu] & 1) ? kKindPos : kKindNeg;
-            byte = (uint8_t)((kind << 3) | lu);
-        }
-        bmap[at] = byte;
-    }
-}
-
-// The same block map, built in place by a whole CTA in shared memory (forward prologue, when the chunk's maps are
-// shared-memory resident): `bm` holds the blocks' region bits (nblocks bytes, as the classifier wrote them) and
-// receives the map.  Every thread of the CTA must call it; it starts and ends with a __syncthreads().
-__host__ __device__ constexpr uint8_t block_map_byte(int r1, int r2, int r3, int r4) {
-    const int r[5] = {0, r1, r2, r3, r4};
-    int lu = 0, le = 0;
-    for (int l = 1; l <= 4; l++) {
-        if (!(r[l] & 4) && (r[l] & 3) != 3) lu = l;
-        if (r[l] == 0) le = l;
-    }
-    if (lu == 0) return 0;
-    const int kind = (le == lu) ? kKindEmpty : (r[lu] & 1) ? kKindPos : kKindNeg;
-    return (uint8_t)((kind << 3) | lu);
-}
-
-// the same function as a table over the four 3-bit region words (r1 | r2 << 3 | r3 << 6 | r4 << 9)
-struct BlockLut { uint8_t v[4096]; };
-constexpr BlockLut make_block_lut() {
-    BlockLut t{};
-    for (int i = 0; i < 4096; i++) t.v[i] = block_map_byte(i & 7, (i >> 3) & 7, (i >> 6) & 7, (i >> 9) & 7);
-    return t;
-}
-__device__ const BlockLut kBlockLut = make_block_lut();
-
-__device__ __forceinline__ void decode3(int i, int nx, int ny, float inv_nx, float inv_ny, int &x, int &y, int &z) {
-    // i = (z * ny + y) * nx + x for i < 2^22: quotients via fp32 reciprocals (exact after the +0.5 nudge)
-    const int q = __float2int_rz(((float)i + 0.5f) * inv_nx);
-    x = i - q * nx;
-    z = __float2int_rz(((float)q + 0.5f) * inv_ny);
-    y = q - z * ny;
-}
-
-__device__ __forceinline__ void smem_or_byte(uint8_t *p, int bits) {
-    const uintptr_t u = reinterpret_cast<uintptr_t>(p);
-    atomicOr(reinterpret_cast<unsigned *>(u & ~(uintptr_t)3), (unsigned)bits << (8 * (int)(u & 3)));
-}
-
-// `tmp` (n8 + n16 + n32 bytes, rounded up to 16) must have been cleared by the CTA before the call.
-__device__ void build_block_map_cta(uint8_t *__restrict__ bm, uint8_t *__restrict__ tmp, const uint8_t *__restrict__ lut,
-                                    int nbx, int nby, int nbz) {
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int nblocks = nbx * nby * nbz;
-    const int ax = (nbx + 1) >> 1, ay = (nby + 1) >> 1, az = (nbz + 1) >> 1;  // 8^3 regions
-    const int cx = (ax + 1) >> 1, cy = (ay + 1) >> 1, cz = (az + 1) >> 1;  // 16^3
-    const int ex = (cx + 1) >> 1, ey = (cy + 1) >> 1;                      // 32^3
-    uint8_t *a8 = tmp, *a16 = a8 + ax * ay * az, *a32 = a16 + cx * cy * cz;
-    __syncthreads();
-    // one pass: every block ORs its region bits into the 8^3 / 16^3 / 32^3 regions around it (shared-memory atomics; most
-    // blocks are empty and contribute nothing)
-    if ((nbx & 3) == 0) {
-        const int wx = nbx >> 2;
-        const float inv_wx = 1.0f / (float)wx, inv_ny = 1.0f / (float)nby;
-        const uint32_t *bm32 = reinterpret_cast<const uint32_t *>(bm);
-        for (int i = tid; i < wx * nby * nbz; i += T) {
-            const uint32_t w = bm32[i];
-            if (w == 0u) continue;
-            int xw, y, z;
-            decode3(i, wx, nby, inv_wx, inv_ny, xw, y, z);
-            const int lo = (int)((w | (w >> 8)) & 7u), hi = (int)(((w >> 16) | (w >> 24)) & 7u);
-            uint8_t *p8 = a8 + ((z >> 1) * ay + (y >> 1)) * ax + 2 * xw;
-            if (lo) smem_or_byte(p8, lo);
-            if (hi) smem_or_byte(p8 + 1, hi);
-            smem_or_byte(a16 + ((z >> 2) * cy + (y >> 2)) * cx + xw, lo | hi);
-            smem_or_byte(a32 + ((z >> 3) * ey + (y >> 3)) * ex + (xw >> 1), lo | hi);
-        }
-    } else {
-        const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
-        for (int i = tid; i < nblocks; i += T) {
-            const int bits = bm[i] & 7;
-            if (bits == 0) continue;
-            int x, y, z;
-            decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
-            smem_or_byte(a8 + ((z >> 1) * ay + (y >> 1)) * ax + (x >> 1), bits);
-            smem_or_byte(a16 + ((z >> 2) * cy + (y >> 2)) * cx + (x >> 2), bits);
-            smem_or_byte(a32 + ((z >> 3) * ey + (y >> 3)) * ex + (x >> 3), bits);
+    for (int r = 0; r < 2; r++) {
+        const int gy = sy * 8 + yl + r, gz = sz * 8 + zl;
+        if (gy < nby && gz < nbz) {
+            const uint8_t *src = marks + (size_t)chunk * bpc + ((size_t)gz * nby + gy) * nbx + xw * 8;
+            for (int k = 0; k < nx; k++) rb[r][k >> 2] |= (uint32_t)__ldcg(src + k) << (8 * (k & 3));
         }
     }
-    __syncthreads();
-    if ((nbx & 3) == 0) {
-        // four blocks of an x row per 32-bit word: they share their 16^3 / 32^3 regions and two 8^3 regions
-        const int wx = nbx >> 2;
-        const float inv_wx = 1.0f / (float)wx, inv_ny = 1.0f / (float)nby;
-        uint32_t *bm32 = reinterpret_cast<uint32_t *>(bm);
-        for (int i = tid; i < wx * nby * nbz; i += T) {
-            int xw, y, z;
-            decode3(i, wx, nby, inv_wx, inv_ny, xw, y, z);
-            const uint32_t w = bm32[i];
-            const int hi = ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + xw] << 6) |
-                           ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (xw >> 1)] << 9);
-            const uint8_t *p8 = a8 + ((z >> 1) * ay + (y >> 1)) * ax + 2 * xw;
-            const int lo0 = (int)p8[0] << 3, lo1 = (int)p8[1] << 3;  // nbx % 4 == 0: both 8^3 regions exist
-            uint32_t out = 0;
+    // region bits per level, byte-parallel.  8^3: x pairs, the lane's two rows, z neighbour (lane ^ 4)
+    auto xpair = [](uint32_t v) { const uint32_t t = v | ((v >> 8) & 0x00ff00ffu); return (t & 0x00ff00ffu) | ((t & 0x00ff00ffu) << 8); };
+    uint32_t r8[2];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                out |= (uint32_t)lut[((w >> (8 * k)) & 7u) | (unsigned)(k < 2 ? lo0 : lo1) | (unsigned)hi] << (8 * k);
-            bm32[i] = out;
-        }
-    } else {
-        const float inv_nx = 1.0f / (float)nbx, inv_ny = 1.0f / (float)nby;
-        for (int i = tid; i < nblocks; i += T) {
-            int x, y, z;
-            decode3(i, nbx, nby, inv_nx, inv_ny, x, y, z);
-            bm[i] = lut[(bm[i] & 7) | ((int)a8[((z >> 1) * ay + (y >> 1)) * ax + (x >> 1)] << 3) |
-                        ((int)a16[((z >> 2) * cy + (y >> 2)) * cx + (x >> 2)] << 6) |
-                        ((int)a32[((z >> 3) * ey + (y >> 3)) * ex + (x >> 3)] << 9)];
+    for (int h = 0; h < 2; h++) {
+        uint32_t v = xpair(rb[0][h] | rb[1][h]);
+        v |= __shfl_xor_sync(kFull, v, 4);
+        r8[h] = v;  // every byte: bits of the 8^3 region of that block
+    }
+    // 16^3: x quad (all four bytes of a half), y quad (lane ^ 1), z quad (lane ^ 4 already in r8, plus lane ^ 8)
+    uint32_t r16[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t v = r8[h];
+        v |= v >> 16; v |= v >> 8; v &= 0xffu;
+        v |= __shfl_xor_sync(kFull, v, 1);
+        v |= __shfl_xor_sync(kFull, v, 8);
+        r16[h] = v;  // one byte: bits of the 16^3 region of this half
+    }
+    // 32^3: both halves, all lanes
+    uint32_t r32 = r16[0] | r16[1];
+    r32 |= __shfl_xor_sync(kFull, r32, 2);
+    r32 |= __shfl_xor_sync(kFull, r32, 16);
+    const uint8_t *__restrict__ lut = kBlockLut.v;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int gy = sy * 8 + yl + r, gz = sz * 8 + zl;
+        if (gy < nby && gz < nbz) {
+            uint8_t *dst = bmap + (size_t)chunk * bpc + ((size_t)gz * nby + gy) * nbx + xw * 8;
+            for (int k = 0; k < nx; k++) {
+                const int h = k >> 2, sh = 8 * (k & 3);
+                dst[k] = __ldg(lut + (((rb[r][h] >> sh) & 7u) | (((r8[h] >> sh) & 7u) << 3) | ((r16[h] & 7u) << 6) | ((r32 & 7u) << 9)));
+            }
         }
     }
-    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -709,8 +637,7 @@ struct ForwardArgs {
     const float *dense;
     const uint2 *vbits;   // [B][vpc]
     const uint8_t *bmap;  // [B][bpc]
-    const uint8_t *marks; // [B][bpc] region bits of the 4^3 blocks
-    size_t vpc, bpc, tmp_bytes;
+    size_t vpc, bpc;
     int wpr;
     int maps_in_smem;
     int32_t *tile_counter;  // [B], zeroed per call
@@ -739,7 +666,7 @@ constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
 __host__ __device__ constexpr size_t fwd_smem_fixed(int warps) { return 128 + (size_t)warps * kStageFloats * sizeof(float); }
 constexpr size_t kFwdSmemFixed = fwd_smem_fixed(kFwdWarpsLarge);  // residency test uses the larger CTA
-constexpr size_t kFwdSmemMax = 232448 - 5120;           // 227 KB opt-in limit per CTA, minus the static shared memory
+constexpr size_t kFwdSmemMax = 232448 - 1024;           // 227 KB opt-in limit per CTA, minus the static shared memory
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -806,20 +733,15 @@ template <bool kLoss, bool kSmemMaps, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const ForwardArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float4 s_steps[kStepEntries];
-    __shared__ __align__(16) uint8_t s_lut[kSmemMaps ? 4096 : 16];  // block_map_byte as a table (block-map build)
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *stage = reinterpret_cast<float *>(smem + 128) + warp * kStageFloats;
     uint2 *s_vbits = reinterpret_cast<uint2 *>(smem + fwd_smem_fixed(kWarps));
     uint8_t *s_bmap = reinterpret_cast<uint8_t *>(s_vbits + a.vpc);
-    uint8_t *s_tmp = s_bmap + a.bpc;
     const unsigned kFull = 0xffffffffu;
     const float kInf = CUDART_INF_F;
 
     if (threadIdx.x < kStepEntries) step_table_fill(s_steps, threadIdx.x, a.inc);
-    if (kSmemMaps)
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x)
-            reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(kBlockLut.v) + i);
     if (kSmemMaps && threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     unsigned phase = 0;
@@ -838,13 +760,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
 
     for (int chunk = blockIdx.x % a.num_chunks; chunk < a.num_chunks; chunk += gridDim.x) {
         if (kSmemMaps) {
-            if (threadIdx.x == 0) {  // cell classes + the blocks' region bits: TMA bulk copies, completion on the mbarrier
+            if (threadIdx.x == 0) {  // cell classes + block map: TMA bulk copies, completion on the mbarrier
                 const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2)), bm_bytes = (unsigned)a.bpc;
                 mbar_expect_tx(mbar, vb_bytes + bm_bytes);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(a.vbits + (size_t)chunk * a.vpc);
                 uint8_t *dst = reinterpret_cast<uint8_t *>(s_vbits);
                 for (unsigned o = 0; o < vb_bytes; o += 32768u) bulk_copy_g2s(dst + o, src + o, min(32768u, vb_bytes - o), mbar);
-                bulk_copy_g2s(s_bmap, a.marks + (size_t)chunk * a.bpc, bm_bytes, mbar);
+                bulk_copy_g2s(s_bmap, a.bmap + (size_t)chunk * a.bpc, bm_bytes, mbar);
             }
         }
         const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
@@ -960,21 +882,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
         TileRay q;
         q.inside = false;
         if (tile < total_tiles) prepare(tile, q);
-#ifdef SPSG_STATS
-        const long long clk_p0 = clock64();
-#endif
-        if (kSmemMaps) {
-            for (int i = threadIdx.x; i < (int)(a.tmp_bytes >> 2); i += blockDim.x) reinterpret_cast<uint32_t *>(s_tmp)[i] = 0u;
-            mbar_wait(mbar, phase);  // the chunk's class planes and region bits have landed
-#ifdef SPSG_STATS
-            const long long clk_p1 = clock64();
-            if (lane == 0) { STAT_ADD(4, clk_p1 - clk_p0); STAT_MAX(5, clk_p1 - clk_p0); }
-#endif
-            build_block_map_cta(s_bmap, s_tmp, s_lut, a.nbx, a.nby, a.nbz);
-#ifdef SPSG_STATS
-            if (lane == 0) { STAT_ADD(6, clock64() - clk_p1); STAT_MAX(7, clock64() - clk_p1); STAT_ADD(13, 1); }
-#endif
-        }
+        if (kSmemMaps) mbar_wait(mbar, phase);  // the chunk's class planes and block map have landed
 
         while (tile < total_tiles) {
             int next = total_tiles;
@@ -1931,30 +1839,14 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     }
     ForwardArgs a;
     memset(&a, 0, sizeof(a));
-    // shared-memory residency of one chunk's maps: class bit planes + block map + the block map builder's scratch
-    size_t tmp_bytes = 0;
-    {
-        int x = L.nbx, y = L.nby, z = L.nbz;
-        for (int l = 0; l < 3; l++) {
-            x = (x + 1) / 2; y = (y + 1) / 2; z = (z + 1) / 2;
-            tmp_bytes += (size_t)x * y * z;
-        }
-        tmp_bytes = align_up(tmp_bytes, 16);
-    }
-    const size_t map_bytes = L.vpc * sizeof(uint2) + L.bpc + tmp_bytes;
+    // shared-memory residency of one chunk's maps: class bit planes + block map
+    const size_t map_bytes = L.vpc * sizeof(uint2) + L.bpc;
     a.maps_in_smem = kFwdSmemFixed + map_bytes <= kFwdSmemMax;
     {
         const dim3 cgrid((unsigned)((L.nby * L.wpr + 3) / 4), (unsigned)L.nbz, (unsigned)p->num_chunks);
-        cell_class_kernel<<<cgrid, 128, 0, st>>>(dense, vbits, L.vpc, marks, p->dimz, p->dimy, p->dimx, L.wpr,
-                                                 L.nby, L.nbx, L.bpc);
+        cell_class_kernel<<<cgrid, 128, 0, st>>>(dense, vbits, L.vpc, marks, p->dimz, p->dimy, p->dimx, L.wpr, L.nby, L.nbx, L.bpc,
+                                                 bmap, (int32_t *)(ws + L.arrive_off), L.nbz);
         CUDA_TRY(cudaGetLastError());
-        if (!a.maps_in_smem) {  // otherwise the forward CTAs build their chunk's block map in shared memory
-            const int sbx = (L.nbx + kSuper - 1) / kSuper, sby = (L.nby + kSuper - 1) / kSuper,
-                      sbz = (L.nbz + kSuper - 1) / kSuper;
-            block_map_kernel<<<(unsigned)(p->num_chunks * sbz * sby * sbx), 512, 0, st>>>(marks, bmap, L.bpc,
-                                                                                          L.nbz, L.nby, L.nbx, sbz, sby, sbx);
-            CUDA_TRY(cudaGetLastError());
-        }
     }
     a.sparse_mapping = sparse_mapping;
     a.vals_sdf = vals_sdf; a.vals_color = vals_color; a.vals_normal = vals_normal; a.vals_semantic = vals_semantic;
@@ -1963,7 +1855,6 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.image_semantic = image_semantic;
     a.mapping3dto2d = mapping3dto2d; a.mapping3dto2d_num = mapping3dto2d_num;
     a.dense = dense; a.vbits = vbits; a.bmap = bmap; a.vpc = L.vpc; a.bpc = L.bpc; a.wpr = L.wpr;
-    a.marks = marks; a.tmp_bytes = tmp_bytes;
     a.tile_counter = (int32_t *)(ws + L.tiles_off);
     a.num_chunks = p->num_chunks;
     a.list_count = (int32_t *)(ws + L.head_off);
