@@ -560,7 +560,12 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
         const int gy = sy * 8 + yl + r, gz = sz * 8 + zl;
         if (gy < nby && gz < nbz) {
             const uint8_t *src = marks + (size_t)chunk * bpc + ((size_t)gz * nby + gy) * nbx + xw * 8;
-            for (int k = 0; k < nx; k++) rb[r][k >> 2] |= (uint32_t)__ldcg(src + k) << (8 * (k & 3));
+            if ((nbx & 7) == 0) {  // rows are 8-byte aligned: one load
+                const uint2 v2 = __ldcg(reinterpret_cast<const uint2 *>(src));
+                rb[r][0] = v2.x; rb[r][1] = v2.y;
+            } else {
+                for (int k = 0; k < nx; k++) rb[r][k >> 2] |= (uint32_t)__ldcg(src + k) << (8 * (k & 3));
+            }
         }
     }
     // region bits per level, byte-parallel.  8^3: x pairs, the lane's two rows, z neighbour (lane ^ 4)
@@ -592,9 +597,17 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
         const int gy = sy * 8 + yl + r, gz = sz * 8 + zl;
         if (gy < nby && gz < nbz) {
             uint8_t *dst = bmap + (size_t)chunk * bpc + ((size_t)gz * nby + gy) * nbx + xw * 8;
-            for (int k = 0; k < nx; k++) {
+            uint32_t out[2] = {0u, 0u};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
                 const int h = k >> 2, sh = 8 * (k & 3);
-                dst[k] = __ldg(lut + (((rb[r][h] >> sh) & 7u) | (((r8[h] >> sh) & 7u) << 3) | ((r16[h] & 7u) << 6) | ((r32 & 7u) << 9)));
+                const uint32_t byte = __ldg(lut + (((rb[r][h] >> sh) & 7u) | (((r8[h] >> sh) & 7u) << 3) | ((r16[h] & 7u) << 6) | ((r32 & 7u) << 9)));
+                out[h] |= byte << sh;
+            }
+            if ((nbx & 7) == 0) {
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(out[0], out[1]);
+            } else {
+                for (int k = 0; k < nx; k++) dst[k] = (uint8_t)(out[k >> 2] >> (8 * (k & 3)));
             }
         }
     }
