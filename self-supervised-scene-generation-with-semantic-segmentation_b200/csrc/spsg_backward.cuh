@@ -1,0 +1,201 @@
+// spsg_backward.cuh -- the backward: gradient-row clearing and the per-(voxel, view) gather, plain or fused with the 2D losses.
+// Fragment of libspsg_raycast.so: included by spsg_raycast.cu INSIDE its anonymous namespace, in the order listed there
+// (one translation unit; every device function is inlined into the kernels that use it).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+
+struct BackwardArgs {
+    const float *grad_color, *grad_depth, *grad_normal, *grad_semantic;  // plain variant
+    const float *image_color, *image_depth, *image_semantic;             // fused-loss variant
+    LossArgs loss;
+    const float *loss_out;
+    float w_depth, w_color, w_sem;
+    const float *grad_scale;  // device scalar or NULL (= 1)
+    const int32_t *mapping3dto2d, *mapping3dto2d_num;
+    float *d_color, *d_depth, *d_normal, *d_semantic;
+    const int32_t *list_count;
+    const int2 *list;
+    int width, height;
+    int views, max_pixels;
+    long long num_locs;
+    int zero_blocks;  // leading CTAs of the launch that clear gradient rows instead of gathering
+    int vec4_ok;      // mapping3dto2d rows are 16-byte aligned
+};
+
+// Clears the 21 gradient slots of voxels [0, N) (replaces the 4 whole-buffer memsets of kernel.cu:557-560): a warp
+// takes 32 consecutive voxels, so every store instruction writes one contiguous run of the AoS arrays.
+// kSkipHit (one view per chunk): rows of voxels that received pixels are left to the gather, which overwrites them.
+template <bool kSkipHit>
+__device__ __forceinline__ void zero_rows(const BackwardArgs &a, long long first_warp, long long num_warps) {
+    const int lane = threadIdx.x & 31;
+    for (long long base = first_warp * 32; base < a.num_locs; base += num_warps * 32) {
+        const long long i = base + lane;
+        const bool keep = kSkipHit && i < a.num_locs && __ldg(a.mapping3dto2d_num + i) > 0;
+        const unsigned kept = __ballot_sync(0xffffffffu, keep);
+        const int n = (int)min((long long)32, a.num_locs - base);
+        float2 *s = reinterpret_cast<float2 *>(a.d_semantic + (size_t)base * 14);
+        for (int e = lane; e < n * 7; e += 32)
+            if (!((kept >> (e / 7)) & 1u)) s[e] = make_float2(0.0f, 0.0f);
+        float *c = a.d_color + (size_t)base * 3, *nm = a.d_normal + (size_t)base * 3;
+        for (int e = lane; e < n * 3; e += 32)
+            if (!((kept >> (e / 3)) & 1u)) {
+                c[e] = 0.0f;
+                nm[e] = 0.0f;
+            }
+        if (lane < n && !keep) a.d_depth[i] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) backward_zero_kernel(const BackwardArgs a) {
+    zero_rows<false>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)gridDim.x * blockDim.x) >> 5);
+}
+
+// Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal).
+// Plain variant: read from the four gradient images.  Fused variant: recomputed from the rendering and the targets
+// of the 2D losses.
+// per-term factors of the fused variant: weight * upstream scale / normaliser (loss_out[4..6]), hoisted out of the pixels
+struct FusedCoef { float sem, col, dep; };
+
+__device__ __forceinline__ FusedCoef fused_coef(const BackwardArgs &a) {
+    FusedCoef c;
+    const float scale = a.grad_scale ? __ldg(a.grad_scale) : 1.0f;
+    c.dep = a.w_depth * a.loss.voxelsize * scale / a.loss_out[4];
+    c.col = a.w_color * scale / a.loss_out[5];
+    c.sem = a.w_sem * scale / a.loss_out[6];
+    return c;
+}
+
+template <bool kFused>
+__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCoef &fc, unsigned gpix, float (&g)[21]) {
+    if (!kFused) {
+        const float2 *s2 = reinterpret_cast<const float2 *>(a.grad_semantic + (size_t)gpix * 14);
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const float2 t = __ldg(s2 + k);
+            g[2 * k] = t.x; g[2 * k + 1] = t.y;
+        }
+        const float *c = a.grad_color + (size_t)gpix * 3, *n = a.grad_normal + (size_t)gpix * 3;
+        g[14] = __ldg(c); g[15] = __ldg(c + 1); g[16] = __ldg(c + 2);
+        g[17] = __ldg(a.grad_depth + gpix);
+        g[18] = __ldg(n); g[19] = __ldg(n + 1); g[20] = __ldg(n + 2);
+    } else {
+        const LossArgs &L = a.loss;
+#pragma unroll
+        for (int k = 0; k < 21; k++) g[k] = 0.0f;
+        // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
+        const int y = L.target_label ? (int)L.target_label[gpix] : 14;
+        if (y < 14) {
+            float l[14];
+            const float2 *s2 = reinterpret_cast<const float2 *>(a.image_semantic + (size_t)gpix * 14);
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                const float2 t = __ldg(s2 + k);
+                l[2 * k] = t.x; l[2 * k + 1] = t.y;
+            }
+            if (l[0] != -CUDART_INF_F) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+                float m = l[0];
+#pragma unroll
+                for (int k = 1; k < 14; k++) m = fmaxf(m, l[k]);
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 14; k++) {
+                    l[k] = expf(l[k] - m);
+                    sum += l[k];
+                }
+                const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+                const float f = fc.sem * w, inv_sum = 1.0f / sum;
+#pragma unroll
+                for (int k = 0; k < 14; k++) g[k] = f * (l[k] * inv_sum - (k == y ? 1.0f : 0.0f));
+            }
+        }
+        if (L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
+            const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float c = __ldg(a.image_color + (size_t)gpix * 3 + k);
+                const float d = __fadd_rn(__fmul_rn(c, w), -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
+                if (c != -CUDART_INF_F) g[14 + k] = fc.col * w * (float)((d > 0.0f) - (d < 0.0f));  // valid = != -inf
+            }
+        }
+        if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
+            const float t = __ldg(L.target_depth + gpix);
+            const float r = __ldg(a.image_depth + gpix);
+            if (t != 0.0f && r != -CUDART_INF_F) {
+                const float d = __fmul_rn(r, L.voxelsize) - t;
+                g[17] = fc.dep * (float)((d > 0.0f) - (d < 0.0f));
+            }
+        }
+    }
+}
+
+// The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
+// warp per item.  Lane k fetches the k-th registered pixel id (one coalesced load) and that pixel's 21 upstream
+// gradients (independent 8- and 4-byte loads), parks them in shared memory, and lane c then adds column c in
+// registration order as grad / count (kernel.cu:398-418) -- a fixed order, so with one view per chunk the result is
+// deterministic and written with plain stores.  With several views per chunk the per-view means of a voxel are summed
+// with float atomics onto rows the zero kernel cleared (kAtomic).
+constexpr int kGatherWarps = 8;
+
+template <bool kFused, bool kAtomic>
+__global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(const BackwardArgs a) {
+    if ((int)blockIdx.x < a.zero_blocks) {
+        zero_rows<true>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)a.zero_blocks * blockDim.x) >> 5);
+        return;
+    }
+    // half a warp per item: 16 lanes cover the typical pixel count of a voxel, the two halves work on different items
+    __shared__ float s_g[kGatherWarps * 2][16 * 21];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hl = lane & 15, half = lane >> 4;
+    const unsigned hmask = 0xffffu << (16 * half);
+    float *tile = s_g[warp * 2 + half];
+    const int groups_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps * 2;
+    const int count = *a.list_count;
+    const unsigned P = (unsigned)(a.width * a.height);
+    int item = (((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp) * 2 + half;
+    int2 e = item < count ? a.list[item] : make_int2(0, 0);
+    FusedCoef fc = {0.0f, 0.0f, 0.0f};
+    if (kFused) fc = fused_coef(a);
+    while (item < count) {
+        const int idx = e.x, img = e.y;
+        const int next_item = item + groups_total;
+        if (next_item < count) e = a.list[next_item];  // prefetch the next pair
+        const size_t row = (size_t)(img % a.views) * a.num_locs + idx;
+        const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
+        const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
+        const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
+        const float inv = __frcp_rn((float)max(cnt, 1));
+        float acc0 = 0.0f, acc1 = 0.0f;  // channels hl and 16 + hl
+        for (int k0 = 0; k0 < cnt; k0 += 16) {
+            const int m = min(16, cnt - k0);
+            if (hl < m) {
+                float g[21];
+                pixel_grads<kFused>(a, fc, pixbase + (unsigned)__ldg(prow + k0 + hl), g);
+#pragma unroll
+                for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
+            }
+            __syncwarp(hmask);
+            for (int r = 0; r < m; r++) {
+                acc0 = __fmaf_rn(tile[r * 21 + hl], inv, acc0);
+                if (hl < 5) acc1 = __fmaf_rn(tile[r * 21 + 16 + hl], inv, acc1);
+            }
+            __syncwarp(hmask);
+        }
+        // channel c -> destination: 0-13 semantic, 14-16 colour, 17 depth->sdf, 18-20 normal
+        float *d0 = hl < 14 ? a.d_semantic + (size_t)idx * 14 + hl : a.d_color + (size_t)idx * 3 + (hl - 14);
+        float *d1 = nullptr;
+        if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
+        else if (hl == 1) d1 = a.d_depth + idx;
+        else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
+        if (kAtomic) {
+            atomicAdd(d0, acc0);
+            if (d1) atomicAdd(d1, acc1);
+        } else {
+            *d0 = acc0;
+            if (d1) *d1 = acc1;
+        }
+        item = next_item;
+    }
+}

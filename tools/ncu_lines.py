@@ -23,7 +23,7 @@ for l in dis.splitlines():
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
-        cur = int(m.group(2)); inl = m.group(3); continue
+        cur = (os.path.basename(m.group(1)), int(m.group(2))); inl = m.group(3); continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         lines.append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
@@ -44,8 +44,10 @@ for k, r in enumerate(body):
     ln = lines[k] if k < len(lines) else -1
     a = agg.setdefault(ln, [0, 0, 0])
     a[0] += int(r[iI]); a[1] += int(r[iS]); a[2] += int(r[iT]); tot += int(r[iI]); totS += int(r[iS])
-src = open(os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "csrc", "spsg_raycast.cu")).read().splitlines()
+CSRC = os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "csrc")
+src = {f: open(os.path.join(CSRC, f)).read().splitlines() for f in os.listdir(CSRC)}
 print("total warp instr %d, samples %d" % (tot, totS))
 for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    text = src[ln - 1].strip()[:100] if ln and 0 < ln <= len(src) else "?"
-    print("%6.2f%% instr  %6.2f%% samples  thr/instr %4.1f  L%-4s %s" % (100.0 * a[0] / tot, 100.0 * a[1] / max(totS, 1), a[2] / max(a[0], 1), ln, text))
+    f, n = ln if isinstance(ln, tuple) else ("?", -1)
+    text = src[f][n - 1].strip()[:100] if f in src and 0 < n <= len(src[f]) else "?"
+    print("%6.2f%% instr  %6.2f%% samples  thr/instr %4.1f  %s:%-4s %s" % (100.0 * a[0] / tot, 100.0 * a[1] / max(totS, 1), a[2] / max(a[0], 1), f.replace("spsg_", "").replace(".cuh", ""), n, text))
