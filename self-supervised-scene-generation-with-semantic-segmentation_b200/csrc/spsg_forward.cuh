@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
         const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
         const uint8_t *bmap = kSmemMaps ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
         Volume v;
-        v.index = a.sparse_mapping + (size_t)chunk * cells;
+        v.index = a.sparse_mapping;
         v.sdf = a.vals_sdf;
-        v.dense = a.dense + (size_t)chunk * cells;
+        v.dense = a.dense;
+        v.cell0 = (unsigned)chunk * (unsigned)cells;
         v.dimx = a.dimx; v.dimy = a.dimy; v.dimz = a.dimz;
         v.guard = a.guard;
 
@@ -402,13 +403,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                                     }
                                 }
                                 if (act <= kActDense) {
-                                    bool valid;
                                     if (act == kActDense) {
                                         dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
-                                        valid = dist == dist;
                                     } else {
-                                        valid = sample_sdf(v, fast_ok, px, py, pz, dist);  // the reference's exact corner arithmetic
+                                        dist = sample_sdf(v, fast_ok, px, py, pz);  // the reference's exact corner arithmetic
                                     }
+                                    const bool valid = dist == dist;
                                     if (valid && ((last_sdf > 0.0f && dist < 0.0f) || (last_sdf < 0.0f && dist > 0.0f))) {  // :205
                                         state = kCross;
                                     } else {
@@ -431,10 +431,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                     if (!__any_sync(kFull, state == kCross)) break;
                     if (state == kCross) {
                         if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
-                            float dl = last_sdf;
-                            if (sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx), __fmaf_rn(r.dy, last_alpha, r.camy),
-                                           __fmaf_rn(r.dz, last_alpha, r.camz), dl))
-                                last_sdf = dl;
+                            const float dl = sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx),
+                                                        __fmaf_rn(r.dy, last_alpha, r.camy), __fmaf_rn(r.dz, last_alpha, r.camz));
+                            if (dl == dl) last_sdf = dl;
                             last_lazy = false;
                         }
                         // findIntersectionBisection (:166-187)
@@ -447,8 +446,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                             cx = __fmaf_rn(r.dx, c, r.camx);
                             cy = __fmaf_rn(r.dy, c, r.camy);
                             cz = __fmaf_rn(r.dz, c, r.camz);
-                            float dc;
-                            if (!sample_sdf(v, fast_ok, cx, cy, cz, dc)) {
+                            const float dc = sample_sdf(v, fast_ok, cx, cy, cz);
+                            if (dc != dc) {
                                 ok = false;
                                 break;
                             }
@@ -460,7 +459,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                             // round(cam + alpha*dir) (:241-242, same fma).  It is one of the 8 present corners; if rounding
                             // ever says otherwise the reference reads stale registers -- we keep marching instead.
                             const int nx = round_voxel(cx), ny = round_voxel(cy), nz = round_voxel(cz);
-                            hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + ((size_t)nz * v.dimy + ny) * v.dimx + nx) : -1;
+                            hit = in_grid(v, nx, ny, nz) ? __ldg(v.index + (v.cell0 + (unsigned)((nz * v.dimy + ny) * v.dimx + nx))) : -1;
                         }
                         if (hit >= 0) {
                             state = kDone;

@@ -152,9 +152,10 @@ __device__ __forceinline__ float step_advance(const float4 *table, float inc, fl
 }
 
 struct Volume {
-    const int32_t *__restrict__ index;  // this chunk's slice of sparse_mapping
+    const int32_t *__restrict__ index;  // sparse_mapping (all chunks)
     const float *__restrict__ sdf;      // vals_sdf
-    const float *__restrict__ dense;    // this chunk's slice of the dense SDF brick (NaN = absent)
+    const float *__restrict__ dense;    // dense SDF brick (all chunks; NaN = absent)
+    unsigned cell0;                     // first cell of this chunk: chunk * dimz * dimy * dimx (all chunks < 2^31 cells)
     int dimx, dimy, dimz;
     float guard;                        // fast corner path needs frac(p) in [guard, 1 - guard] (see frac_guard)
 };
@@ -180,24 +181,34 @@ __device__ __forceinline__ float trilerp(float wx, float wy, float wz, float v00
 }
 
 // trilinearInterpolationSimpleFastFast (kernel.cu:120-156) without the payload: the exact, fully general
-// evaluation (corner coordinates rounded like the reference, index -> value double gather).
-__device__ __noinline__ bool sample_sdf_exact(const Volume &v, float px, float py, float pz, float &dist) {
+// evaluation (corner coordinates rounded like the reference, index -> value double gather).  Out of line and by value:
+// nothing the march keeps in registers has its address taken for this rare path.
+struct SdfSample {
+    float dist;
+    bool valid;
+};
+__device__ __noinline__ SdfSample sample_sdf_exact(const int32_t *__restrict__ index, const float *__restrict__ sdf,
+                                                   int dimx, int dimy, int dimz, float px, float py, float pz) {
+    SdfSample out = {0.0f, false};
     const float qx = __fadd_rn(px, -0.5f), qy = __fadd_rn(py, -0.5f), qz = __fadd_rn(pz, -0.5f);
     const int x0 = round_voxel(qx), y0 = round_voxel(qy), z0 = round_voxel(qz);
     const int x1 = round_voxel(__fadd_rn(qx, 1.0f)), y1 = round_voxel(__fadd_rn(qy, 1.0f)),
               z1 = round_voxel(__fadd_rn(qz, 1.0f));
-    if (!(in_grid(v, x0, y0, z0) && in_grid(v, x1, y1, z1))) return false;
-    const int r00 = (z0 * v.dimy + y0) * v.dimx, r10 = (z0 * v.dimy + y1) * v.dimx;
-    const int r01 = (z1 * v.dimy + y0) * v.dimx, r11 = (z1 * v.dimy + y1) * v.dimx;
-    const int i000 = __ldg(v.index + r00 + x0), i100 = __ldg(v.index + r00 + x1);
-    const int i010 = __ldg(v.index + r10 + x0), i110 = __ldg(v.index + r10 + x1);
-    const int i001 = __ldg(v.index + r01 + x0), i101 = __ldg(v.index + r01 + x1);
-    const int i011 = __ldg(v.index + r11 + x0), i111 = __ldg(v.index + r11 + x1);
-    if ((i000 | i100 | i010 | i110 | i001 | i101 | i011 | i111) < 0) return false;
+    if ((x0 | y0 | z0 | x1 | y1 | z1) < 0 || x0 >= dimx || x1 >= dimx || y0 >= dimy || y1 >= dimy || z0 >= dimz ||
+        z1 >= dimz)
+        return out;
+    const int r00 = (z0 * dimy + y0) * dimx, r10 = (z0 * dimy + y1) * dimx;
+    const int r01 = (z1 * dimy + y0) * dimx, r11 = (z1 * dimy + y1) * dimx;
+    const int i000 = __ldg(index + r00 + x0), i100 = __ldg(index + r00 + x1);
+    const int i010 = __ldg(index + r10 + x0), i110 = __ldg(index + r10 + x1);
+    const int i001 = __ldg(index + r01 + x0), i101 = __ldg(index + r01 + x1);
+    const int i011 = __ldg(index + r11 + x0), i111 = __ldg(index + r11 + x1);
+    if ((i000 | i100 | i010 | i110 | i001 | i101 | i011 | i111) < 0) return out;
     const float wx = __fadd_rn(px, -floorf(px)), wy = __fadd_rn(py, -floorf(py)), wz = __fadd_rn(pz, -floorf(pz));
-    dist = trilerp(wx, wy, wz, __ldg(v.sdf + i000), __ldg(v.sdf + i100), __ldg(v.sdf + i010), __ldg(v.sdf + i001),
-                   __ldg(v.sdf + i110), __ldg(v.sdf + i011), __ldg(v.sdf + i101), __ldg(v.sdf + i111));
-    return true;
+    out.dist = trilerp(wx, wy, wz, __ldg(sdf + i000), __ldg(sdf + i100), __ldg(sdf + i010), __ldg(sdf + i001),
+                       __ldg(sdf + i110), __ldg(sdf + i011), __ldg(sdf + i101), __ldg(sdf + i111));
+    out.valid = true;
+    return out;
 }
 
 // Same result as sample_sdf_exact.  Fast path: when frac(p) is at least `guard` away from 0 and 1 on every axis and
@@ -216,23 +227,27 @@ __device__ __forceinline__ float frac_guard(float guard, int ix, int iy, int iz)
 }
 
 __device__ __forceinline__ float sample_dense(const Volume &v, int ix, int iy, int iz, float wx, float wy, float wz) {
-    const float *__restrict__ b = v.dense + ((size_t)iz * v.dimy + iy) * v.dimx + ix;
-    const int sy = v.dimx, sz = v.dimx * v.dimy;
-    const float v000 = __ldg(b), v100 = __ldg(b + 1), v010 = __ldg(b + sy), v110 = __ldg(b + sy + 1);
-    const float v001 = __ldg(b + sz), v101 = __ldg(b + sz + 1), v011 = __ldg(b + sz + sy), v111 = __ldg(b + sz + sy + 1);
+    // 32-bit offsets from the uniform base pointer: the whole brick is below 2^31 cells (checked on the host)
+    const unsigned sy = (unsigned)v.dimx, sz = (unsigned)(v.dimx * v.dimy);
+    const unsigned o00 = v.cell0 + ((unsigned)iz * (unsigned)v.dimy + (unsigned)iy) * sy + (unsigned)ix;
+    const unsigned o10 = o00 + sy, o01 = o00 + sz, o11 = o01 + sy;
+    const float *__restrict__ b00 = v.dense + o00, *__restrict__ b10 = v.dense + o10;
+    const float *__restrict__ b01 = v.dense + o01, *__restrict__ b11 = v.dense + o11;
+    const float v000 = __ldg(b00), v100 = __ldg(b00 + 1), v010 = __ldg(b10), v110 = __ldg(b10 + 1);
+    const float v001 = __ldg(b01), v101 = __ldg(b01 + 1), v011 = __ldg(b11), v111 = __ldg(b11 + 1);
     return trilerp(wx, wy, wz, v000, v100, v010, v001, v110, v011, v101, v111);
 }
 
-__device__ __forceinline__ bool sample_sdf(const Volume &v, bool fast_ok, float px, float py, float pz, float &dist) {
+// One sample at p: dist when all 8 corners are present, NaN otherwise.  (NaN never satisfies a sign test, so callers
+// treat "valid with a NaN value" and "invalid" alike -- see the note above.)
+__device__ __forceinline__ float sample_sdf(const Volume &v, bool fast_ok, float px, float py, float pz) {
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = __fadd_rn(px, -fx), wy = __fadd_rn(py, -fy), wz = __fadd_rn(pz, -fz);
     const int ix = __float2int_rz(fx), iy = __float2int_rz(fy), iz = __float2int_rz(fz);
     const float g = frac_guard(v.guard, ix, iy, iz);
     const bool fast = fast_ok && fminf(wx, fminf(wy, wz)) >= g && fmaxf(wx, fmaxf(wy, wz)) <= 1.0f - g &&
                       (ix | iy | iz) >= 0 && ix + 1 < v.dimx && iy + 1 < v.dimy && iz + 1 < v.dimz;
-    if (fast) {
-        dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
-        return dist == dist;
-    }
-    return sample_sdf_exact(v, px, py, pz, dist);
+    if (fast) return sample_dense(v, ix, iy, iz, wx, wy, wz);
+    const SdfSample s = sample_sdf_exact(v.index + v.cell0, v.sdf, v.dimx, v.dimy, v.dimz, px, py, pz);
+    return s.valid ? s.dist : __int_as_float(0x7fc00000);
 }
