@@ -68,31 +68,30 @@ class FusedRaycastLossFunction(Function):
         tg = _targets_struct(images, m.height, m.width, target_depth, target_color, weight_color, target_label,
                              class_weight, voxelsize, weights)
         dev = vals_sdf.device
-        if getattr(m, "loss_out", None) is None:
-            m.loss_out = torch.zeros(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+        # terms, total and normalisers of THIS call (the backward reads the normalisers back)
+        loss_out = torch.empty(N.SPSG_LOSS_OUT_FLOATS, device=dev)
         # a backward will follow: let the forward's fill pass clear the gradient rows it will write
         ctx.grads_cleared = any(ctx.needs_input_grad[2:6]) and n > 0
         gb = N.grad_buffers(m.d_color, m.d_depth, m.d_normal, m.d_semantic) if ctx.grads_cleared else None
-        with torch.cuda.device(dev):
+        with rc.device_guard(dev):
             ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
             N.check(N.lib.spsg_raycast_forward_loss(
                 ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
                 N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
                 N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_normal), N.ptr(m.image_semantic),
-                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(m.loss_out),
+                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(loss_out),
                 ctypes.byref(gb) if gb is not None else None, N.ptr(ws), ws.numel(), rc._stream(dev)))
-        ctx.raycaster, ctx.params, ctx.targets, ctx.n = m, p, tg, n
+        ctx.raycaster, ctx.params, ctx.targets, ctx.n, ctx.loss_out = m, p, tg, n, loss_out
         # keep the target tensors alive until backward (the struct only holds raw pointers)
         ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
-        losses = m.loss_out[:4].clone()
         ctx.mark_non_differentiable(m.image_color, m.image_depth, m.image_normal, m.image_semantic)
         imgs = (m.image_color, m.image_depth, m.image_normal, m.image_semantic)
         if images != m.image_depth.shape[0]:
             imgs = tuple(i[:images] for i in imgs)
             ctx.mark_non_differentiable(*imgs)
-        terms = losses[:3]
+        terms = loss_out[:3]
         ctx.mark_non_differentiable(terms)
-        return (losses[3], terms) + imgs
+        return (loss_out[3], terms) + imgs
 
     @staticmethod
     def backward(ctx, grad_total, grad_terms, *unused):
@@ -101,11 +100,11 @@ class FusedRaycastLossFunction(Function):
             p.flags |= N.SPSG_FLAG_GRADS_CLEARED
         dev = m.image_depth.device
         scale = grad_total.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with rc.device_guard(dev):
             ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
             N.check(N.lib.spsg_raycast_backward_loss(
                 ctypes.byref(p), N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_semantic),
-                ctypes.byref(tg), N.ptr(m.loss_out), N.ptr(scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),
+                ctypes.byref(tg), N.ptr(ctx.loss_out), N.ptr(scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),
                 N.ptr(m.mapping3dto2d_num), N.ptr(m.d_color), N.ptr(m.d_depth), N.ptr(m.d_normal), N.ptr(m.d_semantic),
                 N.ptr(ws), ws.numel(), rc._stream(dev)))
         return (None, None, m.d_depth[:n], m.d_color[:n], m.d_normal[:n], m.d_semantic[:n]) + (None,) * 9
@@ -163,7 +162,7 @@ class _Losses2D(Function):
                              voxelsize, weights)
         loss_out = torch.empty(N.SPSG_LOSS_OUT_FLOATS, device=dev)
         scratch = torch.empty(4096, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with rc.device_guard(dev):
             N.check(N.lib.spsg_losses2d_forward(ctypes.byref(tg), N.ptr(image_color), N.ptr(image_depth),
                                                 N.ptr(image_semantic), num_pixels, N.ptr(loss_out), N.ptr(scratch),
                                                 scratch.numel(), rc._stream(dev)))
@@ -171,8 +170,9 @@ class _Losses2D(Function):
         ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
         ctx.save_for_backward(*[t for t in (image_color, image_depth, image_semantic) if t is not None])
         ctx.present = tuple(t is not None for t in (image_color, image_depth, image_semantic))
-        out = loss_out[:4].clone()
-        return out[3], out[:3]
+        terms = loss_out[:3]
+        ctx.mark_non_differentiable(terms)
+        return loss_out[3], terms
 
     @staticmethod
     def backward(ctx, grad_total, grad_terms):
@@ -182,7 +182,7 @@ class _Losses2D(Function):
         need = ctx.needs_input_grad[:3]
         grads = [torch.empty_like(t) if (t is not None and n) else None for t, n in zip(imgs, need)]
         scale = grad_total.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with rc.device_guard(dev):
             N.check(N.lib.spsg_losses2d_backward(ctypes.byref(ctx.targets), N.ptr(imgs[0]), N.ptr(imgs[1]), N.ptr(imgs[2]),
                                                  ctx.num_pixels, N.ptr(ctx.loss_out), N.ptr(scale), N.ptr(grads[0]),
                                                  N.ptr(grads[1]), N.ptr(grads[2]), rc._stream(dev)))

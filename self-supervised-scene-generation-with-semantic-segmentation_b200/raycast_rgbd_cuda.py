@@ -57,6 +57,26 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the context manager costs ~10 us of
+    host time per call, which matters for a 50 us step)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _opt_int(v):
     return int(float(v) + 0.5)  # raycast_rgbd_cuda_kernel.cu:445-456
 
@@ -66,7 +86,7 @@ def construct_dense_sparse_mapping(locs, sparse_mapping):
     _check_input(sparse_mapping, "sparse_mapping")
     _check_dtype(locs, torch.int64, "locs")
     _check_dtype(sparse_mapping, torch.int32, "sparse_mapping")
-    with torch.cuda.device(sparse_mapping.device):
+    with device_guard(sparse_mapping.device):
         N.check(N.lib.spsg_build_index(N.ptr(locs), locs.shape[0], N.ptr(sparse_mapping), sparse_mapping.shape[0],
                                        sparse_mapping.shape[1], sparse_mapping.shape[2], sparse_mapping.shape[3],
                                        _stream(sparse_mapping.device)))
@@ -117,7 +137,7 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
             vals_semantic.numel() < 14 * n:
         raise RuntimeError("voxel value tensors hold fewer than N = %d rows" % n)
     dev = vals_sdf.device
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         nbytes = N.workspace_bytes(p)
         ws = workspace(dev, nbytes, sparse_mapping)
         args = (ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
@@ -159,7 +179,7 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                       max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n,
                       flags=N.SPSG_FLAG_GRADS_CLEARED if grads_cleared else 0)
     dev = grad_color.device
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         ws = workspace(dev, N.workspace_bytes(p), sparse_mapping)
         N.check(N.lib.spsg_raycast_backward(ctypes.byref(p), N.ptr(grad_color), N.ptr(grad_depth), N.ptr(grad_normal),
                                             N.ptr(grad_semantic), N.ptr(sparse_mapping), N.ptr(mapping3dto2d),
@@ -180,6 +200,6 @@ def raycast_occ(occ3d, occ2d, viewMatrixInv, intrinsicParams, opts, flags=0):
                       thresh_sample_dist=0, ray_increment=o[4], dimx=occ3d.shape[4], dimy=occ3d.shape[3],
                       dimz=occ3d.shape[2], num_chunks=occ3d.shape[0], flags=flags)
     dev = occ3d.device
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         N.check(N.lib.spsg_raycast_occ(ctypes.byref(p), N.ptr(occ3d), N.ptr(occ2d), N.ptr(viewMatrixInv),
                                        N.ptr(intrinsicParams), _stream(dev)))
