@@ -21,6 +21,7 @@ __device__ int g_tile_stats[8192][8];  // per tile: total, setup, march, refine,
 #else
 #define STAT_ADD(k, v)
 #define STAT_MAX(k, v)
+#define EVT_ADD(k, v)
 #endif
 
 struct LossArgs {
@@ -50,6 +51,7 @@ struct ForwardArgs {
     int width, height;
     float depth_min, depth_max, thresh, inc;
     int dimx, dimy, dimz;
+    int vx, vy, vz;  // samples with floor(p) in [0, v) per axis can be valid: dim - 1, or 0 when the maps are not in use
     int nbx, nby, nbz;
     int num_chunks, views, max_pixels;
     long long num_locs;
@@ -331,6 +333,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                     while (__any_sync(kFull, state == kMarch)) {
 #ifdef SPSG_STATS
                         my_iters++;
+                        if (lane == 0) EVT_ADD(8, 1);
+                        { const int nm = __popc(__ballot_sync(kFull, state == kMarch)); if (lane == 0) EVT_ADD(14, nm); }
 #endif
                         if (state == kMarch) {
                             if (!(ray < t_end)) {  // kernel.cu:200
@@ -345,8 +349,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                                 // saturates and fails the bounds test below)
                                 const int ix = __float2int_rd(px), iy = __float2int_rd(py), iz = __float2int_rd(pz);
                                 const float fx = (float)ix, fy = (float)iy, fz = (float)iz;
-                                if (skip_ok && (unsigned)ix < (unsigned)a.dimx && (unsigned)iy < (unsigned)a.dimy &&
-                                    (unsigned)iz < (unsigned)a.dimz) {
+                                if ((unsigned)ix < (unsigned)a.vx && (unsigned)iy < (unsigned)a.vy && (unsigned)iz < (unsigned)a.vz) {
                                     // block map and cell class are fetched together (independent shared-memory addresses)
                                     const int b = bmap[((iz >> kFineLog2) * a.nby + (iy >> kFineLog2)) * a.nbx + (ix >> kFineLog2)];
                                     const uint2 word = vbits[(iz * a.dimy + iy) * a.wpr + (ix >> 5)];
@@ -401,7 +404,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                                             }
                                         }
                                     }
+                                } else if (skip_ok) {
+                                    // p < 0 or p >= dim - 1 on some axis: corner 0 rounds to -1 (p - 0.5 <= -0.5 rounds away
+                                    // from zero) or corner 1 to >= dim (p - 0.5, + 1 and + 0.5 are monotonic and exact at
+                                    // dim - 1), so the reference's bounds test (:131) fails -- an invalid sample, no arithmetic.
+                                    // (NaN coordinates convert to 0 and never get here.)
+                                    act = kActInvalid;
                                 }
+                                EVT_ADD(act, 1); EVT_ADD(9, 1); EVT_ADD(10, nadv);
                                 if (act <= kActDense) {
                                     if (act == kActDense) {
                                         dist = sample_dense(v, ix, iy, iz, wx, wy, wz);
@@ -429,7 +439,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
 #endif
                     // ---- refinement round: every lane is either waiting with a crossing or finished
                     if (!__any_sync(kFull, state == kCross)) break;
+                    if (lane == 0) EVT_ADD(11, 1);
                     if (state == kCross) {
+                        EVT_ADD(12, 1);
                         if (last_lazy) {  // the crossing needs the previous sample's value after all (its class says it is valid)
                             const float dl = sample_sdf(v, fast_ok, __fmaf_rn(r.dx, last_alpha, r.camx),
                                                         __fmaf_rn(r.dy, last_alpha, r.camy), __fmaf_rn(r.dz, last_alpha, r.camz));

@@ -180,6 +180,10 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     a.width = p->width; a.height = p->height;
     a.depth_min = p->depth_min; a.depth_max = p->depth_max; a.thresh = p->thresh_sample_dist; a.inc = p->ray_increment;
     a.dimx = p->dimx; a.dimy = p->dimy; a.dimz = p->dimz;
+    {
+        const bool maps = !(p->flags & SPSG_FLAG_NO_BRICK_SKIP) && std::max(p->dimx, std::max(p->dimy, p->dimz)) <= kMaxFastDim;
+        a.vx = maps ? p->dimx - 1 : 0; a.vy = maps ? p->dimy - 1 : 0; a.vz = maps ? p->dimz - 1 : 0;
+    }
     a.nbx = L.nbx; a.nby = L.nby; a.nbz = L.nbz;
     a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
     a.num_locs = p->num_locs;

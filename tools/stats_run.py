@@ -8,7 +8,7 @@ from spsg_b200 import synthetic as S, _native as N
 from spsg_b200.raycast_rgbd import RaycastRGBD
 from tests.common import scene_tensors, views
 dev = torch.device("cuda", 0)
-names = ["exact", "dense", "invalid", "sign", "jumpE", "jumpSame", "", "", "warp_iters", "lane_events", "steps_jumped", "refine_rounds", "refine_lanes"]
+names = ["exact", "dense", "invalid", "sign", "jumpE", "jumpSame", "", "", "warp_iters", "lane_events", "steps_jumped", "refine_rounds", "refine_lanes", "", "march_lanes"]
 for B, F in ((1, 1), (8, 5)):
     batch, t = scene_tensors(list(range(B)), dev)
     n = t["locs"].shape[0]
