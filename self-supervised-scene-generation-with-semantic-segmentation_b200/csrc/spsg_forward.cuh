@@ -530,21 +530,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 // force the payload + atomic results before reading the clock
                 const long long clk_e1 = (col0 != 12345.0f && sem[13] != 12345.0f && !(first && dep == 54321.0f)) ? clock64() : 0;
 #endif
-                {
-                    // the first pixel of a (voxel, view) pair appends the pair to the backward's work list (one atomic
-                    // per warp)
-                    const unsigned m = __ballot_sync(kFull, first);
-#ifdef SPSG_NO_LIST
-                    if (false) {
-#else
-                    if (m) {
+                // the first pixel of a (voxel, view) pair appends the pair to the backward's work list: one atomic per
+                // warp, issued here and consumed after the image stores so that its round trip overlaps them
+                const unsigned list_mask = __ballot_sync(kFull, first);
+                int list_base = 0;
+#ifndef SPSG_NO_LIST
+                if (list_mask && lane == 0) list_base = atomicAdd(a.list_count, __popc(list_mask));
 #endif
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(a.list_count, __popc(m));
-                        base = __shfl_sync(kFull, base, 0);
-                        if (first) a.list[base + __popc(m & ((1u << lane) - 1))] = make_int2(hit, img);
-                    }
-                }
                 if (a.hits && active) a.hits[gpix] = hit;
 #ifdef SPSG_STATS
                 const long long clk_e2 = clock64();
@@ -610,6 +602,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 store_warp_tile<3>(s_nrm, a.image_normal, img, wx0, wy0, a.width, a.height, vec, lane);
                 store_warp_tile<1>(s_dep, a.image_depth, img, wx0, wy0, a.width, a.height, vec, lane);
                 __syncwarp();
+#ifndef SPSG_NO_LIST
+                if (list_mask) {
+                    list_base = __shfl_sync(kFull, list_base, 0);
+                    if (first) a.list[list_base + __popc(list_mask & ((1u << lane) - 1))] = make_int2(hit, img);
+                }
+#endif
 #ifdef SPSG_STATS
                 if (lane == 0) {
                     const long long clk3 = clock64();
