@@ -66,7 +66,10 @@ constexpr int kTilePix = kTileW * kTileH;
 
 constexpr int kWarpW = 8, kWarpH = 4;                   // pixels per warp tile
 constexpr int kFwdWarps = 24;                           // warps of the persistent forward CTA (one CTA per SM)
-constexpr int kFwdWarpsLarge = 28;                      // ... for launches with many tiles per SM (more latency hiding, a few spills)
+#ifndef SPSG_FWD_WARPS_LARGE
+#define SPSG_FWD_WARPS_LARGE 28
+#endif
+constexpr int kFwdWarpsLarge = SPSG_FWD_WARPS_LARGE;                      // ... for launches with many tiles per SM (more latency hiding, a few spills)
 constexpr int kFwdThreads = kFwdWarps * 32;
 constexpr int kStageFloats = 14 * 32;                   // per-warp write-out staging: the widest channel group
 __host__ __device__ constexpr size_t fwd_smem_fixed(int warps) { return 128 + (size_t)warps * kStageFloats * sizeof(float); }
