@@ -47,7 +47,8 @@ for k, r in enumerate(body):
 CSRC = os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "csrc")
 src = {f: open(os.path.join(CSRC, f)).read().splitlines() for f in os.listdir(CSRC)}
 print("total warp instr %d, samples %d" % (tot, totS))
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+bysamples = os.environ.get("BY_SAMPLES") == "1"
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if bysamples else 0])[:top]:
     f, n = ln if isinstance(ln, tuple) else ("?", -1)
     text = src[f][n - 1].strip()[:100] if f in src and 0 < n <= len(src[f]) else "?"
     print("%6.2f%% instr  %6.2f%% samples  thr/instr %4.1f  %s:%-4s %s" % (100.0 * a[0] / tot, 100.0 * a[1] / max(totS, 1), a[2] / max(a[0], 1), f.replace("spsg_", "").replace(".cuh", ""), n, text))
