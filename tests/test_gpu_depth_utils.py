@@ -84,15 +84,30 @@ def test_depth2normals_pipeline_bit_exact(cuda_device, holes):
 
 
 def test_depth2normals_returns_none_when_holes_remain(cuda_device):
+    """A hole wider than the fill rounds can close: Depth2Normals returns None (depth_utils.py:93-95, train.py:537-541).
+
+    Deep inside such a hole the 11x11 window holds fewer than two valid depths, and there the reference kernel indexes
+    one element past its sorted array (depth_utils_cuda_kernel.cu:133, `diameter*diameter-numValid+(numValid+1)/2` = 121):
+    it fills the pixel with whatever the thread's stack held, so its result depends on the kernels that ran before.  This
+    implementation leaves those pixels unfilled (0).  The reference is therefore compared only where it is defined: one
+    median pass, pixels whose window holds at least two valid depths."""
     _need_ref()
+    from spsg_b200 import depth_utils_cuda as mine
     from spsg_b200.depth_utils import Depth2Normals
+    ref = refdriver.depth_module()
     depth, intr = _frames(cuda_device, batch=1, holes=0.0, hole_blocks=False, seed=2)
     depth[:, :, 10:70, 20:100] = 0.0                 # far wider than what one fill round (2 x 5 pixels) can close
     b, _, h, w = depth.shape
-    d_mine, d_ref = depth.clone(), depth.clone()
+    valid_count = torch.nn.functional.avg_pool2d((depth != 0).float(), 11, stride=1, padding=5, divisor_override=1)
+    defined = (depth != 0) | (valid_count > 1.5)
+    assert int((~defined).sum()) > 0
+    ma, mb = torch.zeros_like(depth), torch.zeros_like(depth)
+    mine.median_fill_depthmap(ma, depth)
+    ref.median_fill_depthmap(mb, depth)
+    assert _bits_equal(ma[defined], mb[defined])
+    assert bool((ma[~defined] == 0).all())
+    d_mine = depth.clone()
     mod = Depth2Normals(b, w, h, 5.0, 300.0, max_num_fill_iters=4, device=cuda_device)
-    got = mod(d_mine, intr)
-    want = refdriver.ref_depth2normals(d_ref, intr, torch.zeros_like(depth), torch.zeros(b, h, w, 3, device=cuda_device),
-                                       torch.zeros(b, h, w, 3, device=cuda_device), max_num_fill_iters=4)
-    assert got is None and want is None
-    assert _bits_equal(d_mine, d_ref)                # partially filled, identically
+    assert mod(d_mine, intr) is None
+    assert int((d_mine == 0).sum()) > 0              # partially filled in place, holes remain
+    assert int((d_mine == 0).sum()) < int((depth == 0).sum())
