@@ -109,20 +109,21 @@ struct Stepper {
 };
 
 // The same recurrence with the per-binade constants (they depend on inc only) tabulated once per CTA in shared
-// memory: entry e describes the binade [2^e, 2^(e+1)) as (d, 1/d, lim, -); lim = -inf marks a binade where the closed
-// form is not usable (entry 32 serves every ray parameter outside [1, 2^32)).
+// memory: entry e describes the binade [2^e, 2^(e+1)) as (d, 1/d, lim, top); lim = -inf marks a binade where the closed
+// form is not usable (entry 32 serves every ray parameter outside [1, 2^32); its "top" is 1).
 constexpr int kStepEntries = 33;
 
 __device__ __forceinline__ void step_table_fill(float4 *table, int e, float inc) {
-    float4 t = make_float4(inc, 0.0f, -CUDART_INF_F, 0.0f);
+    float4 t = make_float4(inc, 0.0f, -CUDART_INF_F, 1.0f);
     if (e < 32) {
         const float lo = __uint_as_float((unsigned)(e + 127) << 23), hi = __fmul_rn(lo, 2.0f);
+        t.w = hi;
         const float u = __fmul_rn(lo, 1.1920928955078125e-07f);  // 2^(e-23)
         const float d = __fadd_rn(__fadd_rn(lo, inc), -lo);       // inc on the u grid
         const float rem = __fadd_rn(inc, -d);                     // exact remainder
         const bool regular = (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) && (d > 0.0f) &&
                              (__fmul_rn(fabsf(rem), 2.0f) != u);
-        if (regular) t = make_float4(d, rcp_approx(d), __fadd_rn(hi, -__fmul_rn(inc, 2.0f)), 0.0f);
+        if (regular) t = make_float4(d, rcp_approx(d), __fadd_rn(hi, -__fmul_rn(inc, 2.0f)), hi);
     }
     table[e] = t;
 }
@@ -145,9 +146,13 @@ __device__ __forceinline__ float step_advance(const float4 *table, float inc, fl
             n -= j;
             if (n == 0) return ray;
         }
-        // one real add: the next step of an irregular binade, or the one that crosses the top of this binade
-        ray = __fadd_rn(ray, inc);
-        if (--n == 0) return ray;
+        // real adds: the steps of an irregular binade, or the last ones below the top of this binade and the one that
+        // crosses it (no table look-up until the ray is in the next binade)
+        do {
+            ray = __fadd_rn(ray, inc);
+            --n;
+        } while (n > 0 && ray < t.w);
+        if (n == 0) return ray;
     }
 }
 
