@@ -109,24 +109,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
 }
 
 // Write-out of one channel group of a warp's 8x4 pixel tile: smem [kWarpH][kWarpW*C] -> global rows, by the warp.
+// `pix0` = global pixel index of the tile's first pixel (image * H * W + y0 * W + x0).
 template <int C>
-__device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, float *__restrict__ g, int img, int x0,
+__device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, float *__restrict__ g, size_t pix0, int x0,
                                                 int y0, int width, int height, bool vec, int lane) {
     const int rows = min(kWarpH, height - y0), cols = min(kWarpW, width - x0);
     constexpr int kRow = kWarpW * C;
     if (rows <= 0 || cols <= 0) return;
+    float *__restrict__ base = g + pix0 * C;
+    const int stride = width * C;  // floats between image rows (< 2^31: checked on the host)
     if (vec && cols == kWarpW) {
         constexpr int kVecRow = kRow / 4;
+        // the staged rows are contiguous: element e of the tile is float4 e of the staging buffer
+#pragma unroll 1
         for (int e = lane; e < rows * kVecRow; e += 32) {
             const int r = e / kVecRow, k = e - r * kVecRow;
-            float4 *dst = reinterpret_cast<float4 *>(g + ((size_t)(img * height + y0 + r) * width + x0) * C) + k;
-            __stcs(dst, reinterpret_cast<const float4 *>(s + r * kRow)[k]);
+            __stcs(reinterpret_cast<float4 *>(base + r * stride) + k, reinterpret_cast<const float4 *>(s)[e]);
         }
     } else {
         const int n = cols * C;
+#pragma unroll 1
         for (int e = lane; e < rows * kRow; e += 32) {
             const int r = e / kRow, k = e - r * kRow;
-            if (k < n) __stcs(g + ((size_t)(img * height + y0 + r) * width + x0) * C + k, s[r * kRow + k]);
+            if (k < n) __stcs(base + r * stride + k, s[e]);
         }
     }
 }
@@ -591,19 +596,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 }
                 // the staging buffer is reused: semantic first, then colour + normal + depth
                 const bool vec = a.vec_ok != 0;
+                const size_t tile_pix0 = ((size_t)img * a.height + wy0) * a.width + wx0;
 #pragma unroll
                 for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(stage + lane * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
                 __syncwarp();
-                store_warp_tile<14>(stage, a.image_semantic, img, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<14>(stage, a.image_semantic, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
                 __syncwarp();
                 float *s_col = stage, *s_nrm = stage + 96, *s_dep = stage + 192;
                 s_col[lane * 3 + 0] = col0; s_col[lane * 3 + 1] = col1; s_col[lane * 3 + 2] = col2;
                 s_nrm[lane * 3 + 0] = n0; s_nrm[lane * 3 + 1] = n1; s_nrm[lane * 3 + 2] = n2;
                 s_dep[lane] = dep;
                 __syncwarp();
-                store_warp_tile<3>(s_col, a.image_color, img, wx0, wy0, a.width, a.height, vec, lane);
-                store_warp_tile<3>(s_nrm, a.image_normal, img, wx0, wy0, a.width, a.height, vec, lane);
-                store_warp_tile<1>(s_dep, a.image_depth, img, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<3>(s_col, a.image_color, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<3>(s_nrm, a.image_normal, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
+                store_warp_tile<1>(s_dep, a.image_depth, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
                 __syncwarp();
 #ifndef SPSG_NO_LIST
                 if (list_mask) {
