@@ -39,6 +39,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 MAX_LOCS = 640000  # train.py:136 max_num_locs_per_sample (sizes the reference's memsets)
+E2E_REPEATS = 3   # timed regions of the end-to-end leg (median reported)
 
 
 def parse_args():
@@ -272,20 +273,23 @@ def e2e_ours(ctx, dev, world, steps, warmup, mode="full"):
             step(i, i == n - 1)
 
     run(max(3, warmup))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    run(steps)
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return ms, float(result)
+    times = []
+    for _ in range(E2E_REPEATS):  # host-side jitter is of the order of the step: median of a few timed regions
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(steps)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times.append(ms)
+    return float(np.median(times)), float(result)
 
 
 def roofline_ours(ctx, dev, steps):
@@ -414,7 +418,7 @@ def run_reference(args, dev, rank, world, B, F, num_sets):
     sampler.start()
     ms = timed(step_resident, steps, args.warmup)
     sampler.stop_flag = True
-    ms_e2e = timed(step_e2e, steps, min(args.warmup, 3))
+    ms_e2e = float(np.median([timed(step_e2e, steps, min(args.warmup, 3)) for _ in range(E2E_REPEATS)]))
     return dict(rays=rays, steps=steps, ms=ms, ms_e2e=ms_e2e, clocks=sampler.summary(),
                 h2d=bytes_of(host[0], H2D_KEYS), nv=int(np.mean([d["locs"].shape[0] for d in devsets])))
 
@@ -487,7 +491,7 @@ def main():
                     e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(ctx["host"][0], H2D_KEYS),
                          "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                          "api": "spsg_b200.losses.render_with_2d_losses (fused raycast + depth/colour/semantic losses) "
-                                "+ backward; every step's inputs copied from one packed pinned-host buffer on a copy stream (double-buffered)",
+                                "+ backward; every step's inputs copied from one packed pinned-host buffer on a copy stream (double-buffered); median of %d timed regions" % E2E_REPEATS,
                          "last_loss": last_loss},
                     gpu_launches=ctx["launches_per_step"] * steps, roofline=roof)
         if world == 1 and not args.no_cpu_baseline:
