@@ -340,3 +340,24 @@ def test_crowded_voxels_overflow_max_pixels(cuda_device):
     want_s = g_sem.sum(1) / cnt[rows][:, None]
     assert bool(((sem.grad[rows] - want_s).abs() <= 1e-4 * want_s.abs() + 1e-5).all())
     assert bool((sdf.grad[cnt == 0] == 0).all())
+
+
+def test_oversize_input_is_truncated_like_the_reference_wrapper(cuda_device, capsys):
+    """More voxels than mapping3dto2d has rows: the reference wrapper prints an error and renders the first rows only
+    (locs / sdf / colours / normals cut, vals_semantic not: raycast_rgbd.py:16-21)."""
+    from spsg_b200 import synthetic as S
+    w, h = 96, 80
+    batch, t = scene_tensors([9], cuda_device)
+    n = t["locs"].shape[0]
+    keep = n // 2
+    _, _, view, intr = views(1, 1, cuda_device, seed=9, width=w, height=h)
+    mine = _mine(cuda_device, 1, S.DIMS_ZYX, w, h, keep)
+    ref = _ref(cuda_device, 1, S.DIMS_ZYX, w, h, keep)
+    with torch.no_grad():
+        out_m = mine(t["locs"], t["sdf"], t["color"], t["normal"], t["semantic"], view, intr)
+    assert "ERROR: locs size" in capsys.readouterr().out
+    out_r = ref.forward(t["locs"][:keep].contiguous(), t["sdf"][:keep].contiguous(), t["color"][:keep].contiguous(),
+                        t["normal"][:keep].contiguous(), t["semantic"], view, intr)
+    _assert_render_equal(out_m, out_r, "truncated")
+    assert torch.equal(mine.mapping3dto2d_num[:keep], ref.mapping3dto2d_num[:keep])
+    assert (out_m[1] != NINF).any()
