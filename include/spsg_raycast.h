@@ -244,6 +244,39 @@ SPSG_API int spsg_depth_to_normals(float *depth, const float *intrinsics, float 
                                    int32_t *hole_counts, int32_t batch, int32_t height, int32_t width, float sigma_d,
                                    float sigma_r, int32_t max_fill_iters, void *stream);
 
+/* == Producer glue of the training step (reference torch/train.py:494-509): which voxels of the generator's dense SDF
+ *    head enter the raycaster, in which order, and their payloads.  Replaces
+ *        locs = torch.nonzero((torch.abs(output_sdf.detach()[:, 0]) < truncation) [& ~empty[:, 0]])   train.py:495-497
+ *        locs = torch.cat([locs[:, 1:], locs[:, :1]], 1)                                               train.py:498
+ *        vals = head[locs[:, -1], :, locs[:, 0], locs[:, 1], locs[:, 2]]   for every head              train.py:499-508
+ *    and the index_put backward of those gathers.  Rows come out in torch.nonzero's order (lexicographic in b, z, y, x)
+ *    with columns (z, y, x, b), i.e. exactly the `locs` the raycaster takes.
+ *
+ *    1. spsg_sparsify_count  -> *total_out (device int64) = N; the caller reads it back (the one host synchronisation the
+ *       reference's nonzero has too) and allocates locs (N,4) int64 and the value tensors;
+ *    2. spsg_sparsify_locs   -> locs, using the offsets step 1 left in `scratch`;
+ *    3. spsg_dense_gather    -> sparse[i, c] = dense[b_i, c, z_i, y_i, x_i] for up to 4 heads in one launch;
+ *       spsg_dense_scatter   -> the backward: dense := 0, then dense[b_i, c, z_i, y_i, x_i] = sparse[i, c].
+ *    sdf: (B,Dz,Dy,Dx) float32, 16-byte aligned (channel 0 of a contiguous (B,1,Dz,Dy,Dx) head); empty: same shape,
+ *    one byte per cell (torch.bool), 8-byte aligned, or NULL; cells = B*Dz*Dy*Dx; scratch: caller-owned,
+ *    spsg_sparsify_scratch_bytes(cells) bytes, 256-byte aligned.  |sdf| < truncation is false for NaN, like torch. */
+typedef struct spsg_dense_payload {
+    float *dense;      /* (B, channels, Dz, Dy, Dx) contiguous; read by gather, written by scatter */
+    float *sparse;     /* (N, channels) contiguous; written by gather, read by scatter */
+    int32_t channels;
+    int32_t reserved;
+} spsg_dense_payload;
+SPSG_API size_t spsg_sparsify_scratch_bytes(int64_t cells);
+SPSG_API int spsg_sparsify_count(const float *sdf, const uint8_t *empty, int64_t cells, float truncation, void *scratch,
+                                 size_t scratch_bytes, int64_t *total_out, void *stream);
+SPSG_API int spsg_sparsify_locs(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz, int32_t dimy,
+                                int32_t dimx, float truncation, const void *scratch, int64_t *locs, int64_t num_locs,
+                                void *stream);
+SPSG_API int spsg_dense_gather(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,
+                               int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx, void *stream);
+SPSG_API int spsg_dense_scatter(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,
+                                int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ EXPORTS = (
     "spsg_normals_backward", "spsg_losses2d_forward", "spsg_losses2d_backward",
     "spsg_depth_bilateral_filter", "spsg_depth_median_fill", "spsg_depth_to_cameraspace", "spsg_depth_to_normals",
     "spsg_depth_compute_normals",
+    "spsg_sparsify_scratch_bytes", "spsg_sparsify_count", "spsg_sparsify_locs", "spsg_dense_gather", "spsg_dense_scatter",
 )
 
 
@@ -50,6 +51,12 @@ class LossTargets(ctypes.Structure):
         ("voxelsize", ctypes.c_float), ("weight_depth", ctypes.c_float), ("weight_color_loss", ctypes.c_float),
         ("weight_semantic", ctypes.c_float),
     ]
+
+
+class DensePayload(ctypes.Structure):
+    """``spsg_dense_payload``"""
+    _fields_ = [("dense", ctypes.c_void_p), ("sparse", ctypes.c_void_p), ("channels", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 class GradBuffers(ctypes.Structure):
@@ -107,6 +114,17 @@ def _load():
     lib.spsg_depth_compute_normals.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.spsg_depth_to_normals.restype = ctypes.c_int
     lib.spsg_depth_to_normals.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]
+    dp = ctypes.POINTER(DensePayload)
+    lib.spsg_sparsify_scratch_bytes.restype = sz
+    lib.spsg_sparsify_scratch_bytes.argtypes = [i64]
+    lib.spsg_sparsify_count.restype = ctypes.c_int
+    lib.spsg_sparsify_count.argtypes = [vp, vp, i64, f32, vp, sz, vp, vp]
+    lib.spsg_sparsify_locs.restype = ctypes.c_int
+    lib.spsg_sparsify_locs.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, i64, vp]
+    lib.spsg_dense_gather.restype = ctypes.c_int
+    lib.spsg_dense_gather.argtypes = [dp, i32, vp, i64, i32, i32, i32, i32, vp]
+    lib.spsg_dense_scatter.restype = ctypes.c_int
+    lib.spsg_dense_scatter.argtypes = [dp, i32, vp, i64, i32, i32, i32, i32, vp]
     lib.spsg_timing_enable.restype = None
     lib.spsg_timing_enable.argtypes = [ctypes.c_int]
     lib.spsg_timing_read.restype = ctypes.c_int

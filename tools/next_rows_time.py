@@ -72,3 +72,27 @@ if ref_driver.depth_available():
     print("Depth2Normals, %d frames %dx%d with 3%% holes: reference extension %.0f us, fused pipeline %.0f us" % (
         Bd, Wd, Hd, timeit(lambda: ref_driver.ref_depth2normals(base.clone(), intr8, filt, cam, nrm)),
         timeit(lambda: mod(base.clone(), intr8))))
+
+# ---- producer glue (train.py:494-509): dense heads -> locs + payloads, forward + backward
+from spsg_b200 import sparsify
+dz, dy, dx = S.DIMS_ZYX
+l = t["locs"]
+dense_sdf = torch.full((B, 1, dz, dy, dx), 10.0, device=dev)
+dense_sdf[l[:, 3], 0, l[:, 0], l[:, 1], l[:, 2]] = t["sdf"][:, 0]
+dense_col = torch.rand(B, 3, dz, dy, dx, device=dev)
+dense_sem = torch.randn(B, 14, dz, dy, dx, device=dev)
+def literal():
+    heads = [h.clone().requires_grad_(True) for h in (dense_sdf, dense_col, dense_sem)]
+    locs = torch.nonzero(torch.abs(heads[0].detach()[:, 0]) < S.TRUNCATION)
+    locs = torch.cat([locs[:, 1:], locs[:, :1]], 1)
+    vals = [h[locs[:, -1], :, locs[:, 0], locs[:, 1], locs[:, 2]] for h in heads]
+    sum(v.sum() for v in vals).backward()
+def fused():
+    heads = [h.clone().requires_grad_(True) for h in (dense_sdf, dense_col, dense_sem)]
+    out = sparsify.sparsify_predictions(heads[0], S.TRUNCATION, None, heads[1], heads[2])
+    sum(v.sum() for v in out[1:]).backward()
+def clones():
+    [h.clone().requires_grad_(True) for h in (dense_sdf, dense_col, dense_sem)]
+base = timeit(clones)
+print("dense heads -> locs + sdf/colour/semantic values, fwd+bwd, %d chunks (%d voxels): reference expressions %.0f us, "
+      "sparsify ops %.0f us (both minus %.0f us of head clones)" % (B, n, timeit(literal) - base, timeit(fused) - base, base))
