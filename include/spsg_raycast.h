@@ -277,6 +277,14 @@ SPSG_API int spsg_dense_gather(const spsg_dense_payload *payloads, int32_t count
 SPSG_API int spsg_dense_scatter(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,
                                 int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx, void *stream);
 
+/* == 2D label maps (reference torch/train.py:614-616 target2d_label, :749-752 pred2d_label):
+ *        label = argmax(cat(raycast_semantic, ones), -1).to(uint8)
+ *    = first index of the pixel's maximum among its 14 rendered values if that maximum is >= 1, else 14 (miss or
+ *    unlabeled); NaN counts as the maximum, like torch.max.  semantic: (P,14) float32, 8-byte aligned; labels: P bytes;
+ *    hist: 15 device int64 (cleared, then the number of pixels per label) or NULL. */
+SPSG_API int spsg_labels_from_render(const float *semantic, int64_t num_pixels, uint8_t *labels, int64_t *hist,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ EXPORTS = (
     "spsg_depth_bilateral_filter", "spsg_depth_median_fill", "spsg_depth_to_cameraspace", "spsg_depth_to_normals",
     "spsg_depth_compute_normals",
     "spsg_sparsify_scratch_bytes", "spsg_sparsify_count", "spsg_sparsify_locs", "spsg_dense_gather", "spsg_dense_scatter",
+    "spsg_labels_from_render",
 )
 
 
@@ -125,6 +126,8 @@ def _load():
     lib.spsg_dense_gather.argtypes = [dp, i32, vp, i64, i32, i32, i32, i32, vp]
     lib.spsg_dense_scatter.restype = ctypes.c_int
     lib.spsg_dense_scatter.argtypes = [dp, i32, vp, i64, i32, i32, i32, i32, vp]
+    lib.spsg_labels_from_render.restype = ctypes.c_int
+    lib.spsg_labels_from_render.argtypes = [vp, i64, vp, vp, vp]
     lib.spsg_timing_enable.restype = None
     lib.spsg_timing_enable.argtypes = [ctypes.c_int]
     lib.spsg_timing_read.restype = ctypes.c_int

@@ -19,11 +19,23 @@ from . import _native as N
 from . import raycast_rgbd_cuda as rc
 
 
-def labels_from_render(raycast_semantic):
-    """target2d_label of train.py:614-616 / pred2d_label of :749-752: argmax over cat(render, ones) as uint8,
-    14 = miss or unlabeled.  (Plain tensor ops; not on the timed path.)"""
-    best, arg = raycast_semantic.max(dim=-1)
-    return torch.where(best >= 1.0, arg, torch.full_like(arg, 14)).to(torch.uint8)
+def labels_from_render(raycast_semantic, histogram=False):
+    """target2d_label of train.py:614-616 / pred2d_label of :749-752: ``argmax(cat(render, ones), -1)`` as uint8
+    (14 = miss or unlabeled), shape ``raycast_semantic.shape[:-1]``, in one pass over the rendering.  With
+    ``histogram=True`` also returns the number of pixels per label (15 int64, on the device) from the same pass."""
+    sem = raycast_semantic.detach()
+    rc._check_input(sem, "raycast_semantic")
+    rc._check_dtype(sem, torch.float32, "raycast_semantic")
+    if sem.shape[-1] != 14:
+        raise RuntimeError("raycast_semantic must have 14 channels")
+    if sem.data_ptr() % 8:
+        sem = sem.clone()
+    labels = torch.empty(sem.shape[:-1], dtype=torch.uint8, device=sem.device)
+    hist = torch.empty(15, dtype=torch.int64, device=sem.device) if histogram else None
+    with rc.device_guard(sem.device):
+        N.check(N.lib.spsg_labels_from_render(N.ptr(sem), labels.numel(), N.ptr(labels), N.ptr(hist),
+                                              rc._stream(sem.device)))
+    return (labels, hist) if histogram else labels
 
 
 def _targets_struct(images, h, w, target_depth, target_color, weight_color, target_label, class_weight, voxelsize,

@@ -42,18 +42,59 @@ def window_views(num_views, chunk_dims_zyx, radius=75.0, height=70.0):
     return view, intr
 
 
+def _payload_from_positions(gz, gy, gx, seed):
+    """Deterministic stand-in payload of a voxel from its room coordinates (so that it does not depend on how windows are
+    grouped into launches or dealt to ranks): colour in [0,1)^3 and 14 logits with standard deviation 14."""
+    key = (gz * 73856093) ^ (gy * 19349663) ^ (gx * 83492791) ^ (seed * 2654435761)
+    salts = torch.arange(1, 4 + S.NUM_CLASSES, device=key.device, dtype=torch.int64) * 0x9E3779B97F4A7C1
+    h = key[:, None] * 6364136223846793005 + salts[None, :]          # int64 arithmetic wraps
+    h = (h ^ (h >> 29)) * 0x3F58476D1CE4E5B9
+    h = h ^ (h >> 32)
+    u = ((h >> 11) & 0xFFFFFF).to(torch.float32) / 16777216.0
+    return u[:, :3].contiguous(), ((u[:, 3:] - 0.5) * 48.5).contiguous()
+
+
 def synthetic_predictor(room_sdf, truncation=S.TRUNCATION, seed=0):
     """Stand-in for generator + sparsification (train.py:494-509) on a dense room SDF tensor (Dz,Dy,Dx) that lives on the
-    GPU: returns ``predict(y0, x0, chunk_yx) -> (locs (n,3) int64 z,y,x in chunk coordinates, sdf (n,1), colour (n,3),
-    semantic logits (n,14))``."""
+    GPU.  The "generator heads" are dense room volumes made once: the SDF itself, a colour volume (3 channels) and a
+    logit volume (14 channels), both a fixed function of the voxel's room coordinates (so a window's payload does not
+    depend on launch grouping or rank).  Returns ``predict(y0, x0, chunk_yx) -> (locs (n,3) int64 z,y,x in chunk
+    coordinates, sdf (n,1), colour (n,3), semantic logits (n,14))``; ``predict.predict_group(windows, chunk_yx) -> (locs
+    (n,4) with b = index into windows, sdf, colour, logits)`` does a whole launch group at once: the windows' heads are
+    stacked as dense (B,C,Dz,cy,cx) batches, like a generator's output, and go through ``sparsify.sparsify_predictions``
+    (one host synchronisation per group)."""
+    from . import sparsify
+    dz, dy, dx = room_sdf.shape
+    dev = room_sdf.device
+    gz, gy, gx = torch.meshgrid(torch.arange(dz, device=dev), torch.arange(dy, device=dev), torch.arange(dx, device=dev),
+                                indexing="ij")
+    color, sem = _payload_from_positions(gz.reshape(-1), gy.reshape(-1), gx.reshape(-1), seed)
+    room_color = color.t().reshape(3, dz, dy, dx).contiguous()
+    room_sem = sem.t().reshape(S.NUM_CLASSES, dz, dy, dx).contiguous()
+    del gz, gy, gx, color, sem
+    outside = 2.0 * truncation + 1.0
+
     def predict(y0, x0, chunk_yx):
         win = room_sdf[:, y0:y0 + chunk_yx[0], x0:x0 + chunk_yx[1]]
         locs = torch.nonzero(win.abs() < truncation)
-        vals = win[locs[:, 0], locs[:, 1], locs[:, 2]].reshape(-1, 1).contiguous()
-        g = torch.Generator(device=win.device).manual_seed(seed * 1000003 + y0 * 4099 + x0)
-        color = torch.rand(locs.shape[0], 3, device=win.device, generator=g)
-        sem = torch.randn(locs.shape[0], S.NUM_CLASSES, device=win.device, generator=g) * 14.0
-        return locs, vals, color, sem
+        z, y, x = locs[:, 0], locs[:, 1] + y0, locs[:, 2] + x0
+        return (locs, room_sdf[z, y, x].reshape(-1, 1).contiguous(), room_color[:, z, y, x].t().contiguous(),
+                room_sem[:, z, y, x].t().contiguous())
+
+    def predict_group(windows, chunk_yx):
+        B = len(windows)
+        head_sdf = torch.full((B, 1, dz, chunk_yx[0], chunk_yx[1]), outside, device=dev)
+        head_col = torch.zeros(B, 3, dz, chunk_yx[0], chunk_yx[1], device=dev)
+        head_sem = torch.zeros(B, S.NUM_CLASSES, dz, chunk_yx[0], chunk_yx[1], device=dev)
+        for b, (y0, x0) in enumerate(windows):
+            ys, xs = slice(y0, y0 + chunk_yx[0]), slice(x0, x0 + chunk_yx[1])
+            win = room_sdf[:, ys, xs]                                           # smaller at the room border
+            head_sdf[b, 0, :, :win.shape[1], :win.shape[2]] = win
+            head_col[b, :, :, :win.shape[1], :win.shape[2]] = room_color[:, :, ys, xs]
+            head_sem[b, :, :, :win.shape[1], :win.shape[2]] = room_sem[:, :, ys, xs]
+        return sparsify.sparsify_predictions(head_sdf, truncation, None, head_col, head_sem)
+
+    predict.predict_group = predict_group
     return predict
 
 
@@ -72,35 +113,50 @@ def render_room(predict, room_dims_zyx, device, views_per_chunk=5, chunks_per_la
     view = torch.from_numpy(np.tile(view_np, (B, 1, 1))).to(device)
     intr = torch.from_numpy(np.tile(intr_np, (B, 1))).to(device)
     grid2cam = torch.inverse(view[::F]).contiguous()          # one rotation per chunk for the normals (train.py:544)
-    hist = torch.zeros(S.NUM_CLASSES + 1, dtype=torch.float64, device=device)
+    hist = torch.zeros(S.NUM_CLASSES + 1, dtype=torch.int64, device=device)
     images, rendered, rays = [], 0, 0
+    predict_group = getattr(predict, "predict_group", None)
     for s in range(0, len(mine), B):
         group = mine[s:s + B]
-        parts = [predict(y0, x0, chunk_yx) for (y0, x0) in group]
-        keep = [k for k, p in enumerate(parts) if p[0].shape[0] > 0]   # the reference skips empty windows (:160-161)
-        if not keep:
+        if predict_group is not None:
+            # the whole group at once; chunk slot b = position in the group, windows without voxels keep an idle slot
+            locs, sdf, color, sem = predict_group(group, chunk_yx)
+            edges = torch.searchsorted(locs[:, 3].contiguous(), torch.arange(len(group) + 1, device=device)).tolist()
+            present = [b for b in range(len(group)) if edges[b + 1] > edges[b]]   # rows are sorted by chunk
+            slots = len(group)
+        else:
+            parts = [predict(y0, x0, chunk_yx) for (y0, x0) in group]
+            present = [k for k, p in enumerate(parts) if p[0].shape[0] > 0]
+            slots = len(present)
+            if present:  # non-empty windows packed into consecutive chunk slots
+                locs = torch.cat([torch.cat([parts[k][0], torch.full((parts[k][0].shape[0], 1), b, dtype=torch.long,
+                                                                     device=device)], 1)
+                                  for b, k in enumerate(present)]).contiguous()
+                sdf = torch.cat([parts[k][1] for k in present])
+                color = torch.cat([parts[k][2] for k in present])
+                sem = torch.cat([parts[k][3] for k in present])
+        if not present:  # the reference skips empty windows (test_scene_as_chunks.py:160-161)
             continue
-        # chunks of a partial last group are padded by repeating nothing: the launch renders B slots, empty ones miss
-        locs = torch.cat([torch.cat([parts[k][0], torch.full((parts[k][0].shape[0], 1), b, dtype=torch.long, device=device)], 1)
-                          for b, k in enumerate(keep)]).contiguous()
-        sdf = torch.cat([parts[k][1] for k in keep])
-        color = torch.cat([parts[k][2] for k in keep])
-        sem = torch.cat([parts[k][3] for k in keep])
         with torch.no_grad():
             normals = compute_normals_sparse(locs, sdf, chunk_dims, grid2cam, num_chunks=B)
             _, depth, _, sem_img = rc(locs, sdf, color, normals, sem, view, intr)
-            nimg = len(keep) * F
-            labels = labels_from_render_logits(sem_img[:nimg], depth[:nimg])
-            hist += torch.bincount(labels.reshape(-1).long(), minlength=S.NUM_CLASSES + 1).to(torch.float64)
-        rendered += len(keep)
-        rays += nimg * width * height
+            # pred2d_label of train.py:749-752 and its per-class pixel counts in one pass over the rendering
+            labels, h = labels_from_render(sem_img[:slots * F], histogram=True)
+            labels = labels.view(slots, F, height, width)
+            if len(present) < slots:  # idle slots rendered nothing: all their pixels are label 14
+                h[S.NUM_CLASSES] -= (slots - len(present)) * F * width * height
+                labels = labels[torch.tensor(present, device=device)]
+            hist += h
+        rendered += len(present)
+        rays += len(present) * F * width * height
         if keep_images:
-            for b, k in enumerate(keep):
-                images.append((group[k], labels[b * F:(b + 1) * F].cpu()))
+            for j, k in enumerate(present):
+                images.append((group[k], labels[j].cpu()))
     total_hist = hist.clone()
     if world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.all_reduce(total_hist)   # the only collective: 15 counters
-    return dict(windows=len(windows), rendered_windows=rendered, rays=rays, label_hist=total_hist.cpu().numpy(),
+    return dict(windows=len(windows), rendered_windows=rendered, rays=rays,
+                label_hist=total_hist.cpu().numpy().astype(np.float64),
                 images=images)
 
 

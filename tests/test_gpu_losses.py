@@ -146,3 +146,27 @@ def test_standalone_image_losses_match_literal_pytorch(cuda_device):
         assert scale > 0, name
         assert float((ga - gb).abs().max()) <= 1e-4 * scale, name
         assert bool((b.grad[~valid] == 0).all()), name
+
+
+def test_label_maps_match_the_literal_expression(cuda_device):
+    """train.py:614-616 / :749-752: argmax(cat(render, ones), -1) as uint8 -- ties, values exactly 1, misses (-inf),
+    unlabeled (all zero), NaN, and the per-class pixel counts of the same pass."""
+    from spsg_b200.losses import labels_from_render
+    g = torch.Generator().manual_seed(3)
+    sem = torch.randn(5, 37, 41, 14, generator=g) * 2.0
+    flat = sem.view(-1, 14)
+    flat[0::7] = -float("inf")                                   # misses
+    flat[1::7] = 0.0                                             # unlabeled target voxel
+    flat[2::7] = torch.nn.functional.one_hot(torch.arange(flat[2::7].shape[0]) % 14, 14).float()   # one-hot: max == 1 (tie with the appended 1)
+    flat[3::7, 5] = flat[3::7, 9] = 4.0                          # two equal maxima: the first wins
+    flat[4::49, 3] = float("nan")
+    flat[5::49, 0] = 0.99999994                                  # just below 1
+    sem = sem.to(cuda_device)
+    cat = torch.cat((sem, torch.ones(sem.shape[:-1] + (1,), device=cuda_device)), dim=-1)
+    want = torch.max(cat, dim=-1)[1].to(torch.uint8)
+    got, hist = labels_from_render(sem, histogram=True)
+    assert got.dtype == torch.uint8 and got.shape == want.shape
+    assert torch.equal(got, want)
+    assert torch.equal(hist, torch.bincount(want.reshape(-1).long(), minlength=15))
+    assert torch.equal(labels_from_render(sem), want)
+    assert labels_from_render(sem[:0]).shape == (0, 37, 41)

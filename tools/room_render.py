@@ -34,7 +34,7 @@ rendered = P.sum_over_ranks(out["rendered_windows"]); rays = P.sum_over_ranks(ou
 if rank == 0:
     print(json.dumps({"workload": "room %dx%dx%d, %d windows (64x64 stride 32), %d views 320x256 per window" % (*args.room, out["windows"], args.views),
                       "n_gpus": world, "ms_per_room": ms, "windows_per_s": rendered / (ms * 1e-3), "rays_per_s": rays / (ms * 1e-3),
-                      "includes": "sparsification (nonzero + gathers), normals, raycast forward, label argmax + histogram",
+                      "includes": "window head assembly, sparsification (spsg sparsify ops), normals, raycast forward, fused label map + histogram",
                       "label_hist": [int(v) for v in out["label_hist"]]}))
 if world > 1:
     torch.distributed.destroy_process_group()
