@@ -194,3 +194,47 @@ def test_backward_on_soup_matches_reference(cuda_device):
         scale = float(b.abs().max().item()) + 1e-12
         err = float((a - b).abs().max().item()) / scale
         assert err < 1e-3, "%s gradient: max error %.3g of the largest entry" % (name, err)
+
+
+def test_fused_losses_on_soup_match_literal_pytorch(cuda_device):
+    """The fused raycast + 2D losses on a noisy scene with random targets (holes, ignore labels, per-pixel colour weights,
+    one image without a single hit) against the literal expressions on the un-fused rendering."""
+    from oracle import losses_ref as R
+    from spsg_b200.losses import render_with_2d_losses
+    from spsg_b200.raycast_rgbd import RaycastRGBD
+    dims = (24, 24, 24)
+    w, h = 64, 48
+    B = 3
+    t, n = _batch(dims, [(31, "noise"), (32, "blocky"), None], cuda_device)      # the third chunk is empty: no hits
+    view = _cameras(dims, B, 3, cuda_device)
+    intr = torch.tensor([[50.0, 50.0, 31.5, 23.5]] * B, device=cuda_device)
+    rc = RaycastRGBD(B, dims, w, h, 0.0, 150.0, 50.0, 0.9, max_num_frames=1, max_num_locs_per_sample=n, device=cuda_device)
+    g = torch.Generator().manual_seed(4)
+    images_depth = (torch.rand(B, 1, h, w, generator=g) * 2.0)
+    images_depth[torch.rand(B, 1, h, w, generator=g) < 0.2] = 0.0
+    images_color = torch.rand(B, h, w, 3, generator=g)
+    label = torch.randint(0, 15, (B, h, w, 1), generator=g).to(torch.uint8)
+    wc = torch.rand(B, 1, h, w, generator=g) + 0.5
+    cw = torch.rand(14, generator=g) + 0.1
+    images_depth, images_color, label, wc, cw = (x.to(cuda_device) for x in (images_depth, images_color, label, wc, cw))
+
+    def leafs():
+        return [t[k].clone().requires_grad_(True) for k in ("sdf", "color", "semantic")]
+
+    sdf, col, sem = leafs()
+    r_color, r_depth, _, r_sem = rc(t["locs"], sdf, col, t["normal"], sem, view, intr)
+    assert (r_depth[:2] != NINF).any() and bool((r_depth[2] == NINF).all())
+    total = 0.5 * R.depth_l1_loss(r_depth, images_depth, 0.02) + 1.5 * R.compute_2dcolor_loss(r_color, images_color, wc) + \
+        0.8 * R.semantic_2d_ce_loss(r_sem, label, cw)
+    total.backward()
+    want = [x.grad.clone() for x in (sdf, col, sem)]
+    sdf2, col2, sem2 = leafs()
+    total2, terms2, _ = render_with_2d_losses(rc, t["locs"], sdf2, col2, t["normal"], sem2, view, intr,
+                                              images_depth=images_depth, images_color=images_color, weight_color=wc,
+                                              target2d_label=label, weight_semantic_class=cw, voxelsize=0.02,
+                                              weight_depth_loss=0.5, weight_color_loss=1.5, weight_semantic_loss=0.8)
+    total2.backward()
+    torch.testing.assert_close(total2.detach(), total.detach(), rtol=1e-5, atol=1e-7)
+    for name, a, b in zip(("sdf", "color", "semantic"), (sdf2.grad, col2.grad, sem2.grad), want):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 1e-3 * scale, "%s gradient: max error %.3g of %.3g" % (name, float((a - b).abs().max()), scale)
