@@ -1,7 +1,7 @@
 """Device time of the producer / consumer ops next to the raycast (SURVEY 8f-1 and rows a11-a13 un-fused) against the
 reference's literal PyTorch expressions (oracle/losses_ref.py), C3-sized inputs."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it times the checkers next to the product)
 sys.path.insert(0, ROOT)
 import torch
 from oracle import losses_ref as R

@@ -1,7 +1,7 @@
 """Quick device timing of mine vs the reference extension on configs C2 / C3 (development aid, not the bench)."""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it times the checkers next to the product)
 sys.path.insert(0, ROOT)
 from spsg_b200 import synthetic as S
 from spsg_b200.raycast_rgbd import RaycastRGBD
