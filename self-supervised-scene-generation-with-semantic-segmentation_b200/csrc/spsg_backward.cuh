@@ -22,7 +22,6 @@ struct BackwardArgs {
     int views, max_pixels;
     long long num_locs;
     int zero_blocks;  // leading CTAs of the launch that clear gradient rows instead of gathering
-    int vec4_ok;      // mapping3dto2d rows are 16-byte aligned
 };
 
 // Clears the 21 gradient slots of voxels [0, N) (replaces the 4 whole-buffer memsets of kernel.cu:557-560): a warp

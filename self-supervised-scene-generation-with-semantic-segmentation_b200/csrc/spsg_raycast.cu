@@ -280,7 +280,6 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     a.width = p->width; a.height = p->height;
     a.views = p->views_per_chunk; a.max_pixels = p->max_pixels_per_voxel;
     a.num_locs = p->num_locs;
-    a.vec4_ok = (p->max_pixels_per_voxel % 4 == 0) && aligned16(mapping3dto2d);
     const int sms = sm_count();
     // half a warp per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
     const long long max_items = p->num_locs * p->views_per_chunk;
