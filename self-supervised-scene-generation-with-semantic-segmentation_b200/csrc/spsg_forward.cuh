@@ -59,6 +59,8 @@ struct ForwardArgs {
     int vec_ok;  // image rows 16-byte aligned: float4 write-out allowed
     float guard; // see frac_guard
     LossArgs loss;
+    spsg_grad_buffers clear;  // gradient rows [0, clear_rows) to zero for the backward that follows (or clear_rows = 0)
+    long long clear_rows;
 };
 
 constexpr int kTileW = 16, kTileH = 8;  // pixels per CTA of the occupancy kernel: 4 warps of 8x4 pixels
@@ -136,6 +138,18 @@ __device__ __forceinline__ void store_warp_tile(const float *__restrict__ s, flo
     }
 }
 
+// words [0, n) of p := 0, this warp's share of a launch-wide sweep: 16-byte stores where p is aligned
+__device__ __forceinline__ void clear_span(float *__restrict__ p, size_t n, size_t warp_id, size_t num_warps, int lane) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+        const size_t n4 = n >> 2;
+        float4 *p4 = reinterpret_cast<float4 *>(p);
+        for (size_t i = warp_id * 32 + lane; i < n4; i += num_warps * 32) p4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (warp_id == 0 && lane < (int)(n & 3)) p[(n4 << 2) + lane] = 0.0f;
+    } else {
+        for (size_t i = warp_id * 32 + lane; i < n; i += num_warps * 32) p[i] = 0.0f;
+    }
+}
+
 // Persistent forward: one CTA per SM, one thread per ray, one 8x4-pixel tile per warp at a time.
 // kernel.cu:265-297 (init + ray), :190-263 (march), :166-187 (regula falsi), :215-249 (hit write-out + voxel->pixel
 // registration); kLoss adds the 2D losses (train.py:635-638, loss.py:246-257, train.py:744-746) to the epilogue.
@@ -154,6 +168,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
     const unsigned kFull = 0xffffffffu;
     const float kInf = CUDART_INF_F;
 
+    if (a.clear_rows > 0) {
+        // The backward's output rows are zeroed here (the reference memsets its whole d_* buffers, kernel.cu:557-560): a few
+        // fire-and-forget stores per warp that overlap the march, instead of a longer fill pass in front of the index build.
+        const size_t wid = (size_t)blockIdx.x * kWarps + warp, nw = (size_t)gridDim.x * kWarps, n = (size_t)a.clear_rows;
+        clear_span(a.clear.d_semantic, n * 14, wid, nw, lane);
+        clear_span(a.clear.d_color, n * 3, wid, nw, lane);
+        clear_span(a.clear.d_normal, n * 3, wid, nw, lane);
+        clear_span(a.clear.d_depth, n, wid, nw, lane);
+    }
     if (threadIdx.x < kStepEntries) step_table_fill(s_steps, threadIdx.x, a.inc);
     if (kSmemMaps && threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();

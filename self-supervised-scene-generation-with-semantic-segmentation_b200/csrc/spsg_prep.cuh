@@ -7,9 +7,9 @@
 // per-call preparation: fill, index + dense brick, cell classes, block map
 // ---------------------------------------------------------------------------------------------
 
-// One launch instead of the reference's memsets (kernel.cu:475,483,515 and, when the gradient buffers are handed to
-// the forward, :557-560): up to kFillRegions word-filled regions.
-constexpr int kFillRegions = 7;
+// One launch instead of the reference's memsets (kernel.cu:475,483,515): up to kFillRegions word-filled regions.
+// (The gradient rows of kernel.cu:557-560 are zeroed by the forward kernel's warps, see raycast_forward_kernel.)
+constexpr int kFillRegions = 3;
 struct FillArgs {
     uint32_t *ptr[kFillRegions];
     size_t words[kFillRegions];

@@ -126,18 +126,10 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         f.ptr[0] = build_index ? (uint32_t *)sparse_mapping : nullptr; f.words[0] = cells; f.value[0] = 0xffffffffu;
         f.ptr[1] = (uint32_t *)dense; f.words[1] = L.dense_bytes / 4; f.value[1] = 0xffffffffu;
         f.ptr[2] = (uint32_t *)(ws + L.zero_off); f.words[2] = L.zero_bytes / 4; f.value[2] = 0u;
-        size_t grad_words = 0;
-        if (clear_grads && p->num_locs > 0) {  // rows [0, N) of the backward's outputs (kernel.cu:557-560)
-            if (!clear_grads->d_color || !clear_grads->d_depth || !clear_grads->d_normal || !clear_grads->d_semantic)
-                return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer in clear_grads");
-            const size_t n = (size_t)p->num_locs;
-            f.ptr[3] = (uint32_t *)clear_grads->d_semantic; f.words[3] = n * 14;
-            f.ptr[4] = (uint32_t *)clear_grads->d_color; f.words[4] = n * 3;
-            f.ptr[5] = (uint32_t *)clear_grads->d_normal; f.words[5] = n * 3;
-            f.ptr[6] = (uint32_t *)clear_grads->d_depth; f.words[6] = n;
-            grad_words = n * 21;
-        }
-        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4 + grad_words) / 4;
+        if (clear_grads && p->num_locs > 0 &&
+            (!clear_grads->d_color || !clear_grads->d_depth || !clear_grads->d_normal || !clear_grads->d_semantic))
+            return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer in clear_grads");
+        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4) / 4;
         const unsigned blocks = (unsigned)std::min<size_t>((vecs + 1023) / 1024 + 1, (size_t)sms * 8);
         fill_kernel<<<blocks, 256, 0, st>>>(f);
         CUDA_TRY(cudaGetLastError());
@@ -196,6 +188,10 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         a.guard = std::min(kFracGuard, std::max(ldexpf(1.0f, k - 21), ldexpf(1.0f, -18)));  // 8 ulp of the largest coordinate
     }
     a.loss = make_loss_args(targets, accum);
+    if (clear_grads && p->num_locs > 0) {  // rows [0, N) of the backward's outputs (kernel.cu:557-560), cleared by the forward's warps
+        a.clear = *clear_grads;
+        a.clear_rows = p->num_locs;
+    }
     // persistent: one CTA per SM (fewer when there is less than one tile per warp)
     const long long tiles_x = (p->width + kWarpW - 1) / kWarpW, tiles_y = (p->height + kWarpH - 1) / kWarpH;
     const long long all_tiles = ((tiles_x + 1) / 2) * ((tiles_y + 1) / 2) * 4 * p->views_per_chunk * p->num_chunks;
