@@ -106,37 +106,28 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
     const int yb = w / wpr, xw = w - yb * wpr;
     const int zb = blockIdx.y, chunk = blockIdx.z;
     const int y0 = yb * kFine, z0 = zb * kFine;
-    const float *__restrict__ base = dense + (size_t)chunk * dimz * dimy * dimx;
-    const int x = xw * 32 + lane, xn = xw * 32 + 32;
-    // voxel rows (y0..y0+4, z0..z0+4): value of this lane's voxel, and of the first voxel of the next word for lane 0
-    float val[5][5], nxt[5][5];
-#pragma unroll
-    for (int dz = 0; dz < 5; dz++)
-#pragma unroll
-        for (int dy = 0; dy < 5; dy++) {
-            const int y = y0 + dy, z = z0 + dz;
-            const bool row = y < dimy && z < dimz;
-            const size_t o = ((size_t)z * dimy + y) * dimx;
-            val[dz][dy] = (row && x < dimx) ? __ldg(base + o + x) : CUDART_NAN_F;
-            nxt[dz][dy] = (row && lane == 0 && xn < dimx) ? __ldg(base + o + xn) : CUDART_NAN_F;
-        }
-    // per voxel row: present / positive-class / negative-class masks over x, shifted so that bit x also covers x+1
+    // 32-bit cell offsets from the brick's base (the whole brick is below 2^31 cells, checked on the host)
+    const unsigned plane = (unsigned)dimy * (unsigned)dimx;
+    const unsigned x = (unsigned)(xw * 32 + lane);
+    const bool in_x = x < (unsigned)dimx, in_x1 = x + 1u < (unsigned)dimx;
+    const unsigned o00 = ((unsigned)chunk * (unsigned)dimz + (unsigned)z0) * plane + (unsigned)y0 * (unsigned)dimx + x;
+    // Per voxel row (y0..y0+4, z0..z0+4): every lane loads its voxel and the next one in x (two coalesced loads), so
+    // "voxels x and x+1 are both present / positive-class / negative-class" is a lane-local test and one ballot per mask.
     unsigned pres[5][5], posm[5][5], negm[5][5];
 #pragma unroll
     for (int dz = 0; dz < 5; dz++)
 #pragma unroll
         for (int dy = 0; dy < 5; dy++) {
-            const float a = val[dz][dy], n = nxt[dz][dy];
-            const unsigned p = __ballot_sync(kFull, a == a), pp = __ballot_sync(kFull, a > kTiny && a < kHuge),
-                           pn = __ballot_sync(kFull, a < -kTiny && a > -kHuge);
-            // lane 0 holds the next word's first voxel
-            const unsigned np = __shfl_sync(kFull, (unsigned)(n == n), 0), npp = __shfl_sync(kFull, (unsigned)(n > kTiny && n < kHuge), 0),
-                           npn = __shfl_sync(kFull, (unsigned)(n < -kTiny && n > -kHuge), 0);
-            pres[dz][dy] = p & ((p >> 1) | (np << 31));
-            posm[dz][dy] = pp & ((pp >> 1) | (npp << 31));
-            negm[dz][dy] = pn & ((pn >> 1) | (npn << 31));
+            const bool row = y0 + dy < dimy && z0 + dz < dimz;
+            const float *__restrict__ q = dense + (o00 + (unsigned)dz * plane + (unsigned)dy * (unsigned)dimx);
+            const float a = (row && in_x) ? __ldg(q) : CUDART_NAN_F;
+            const float n = (row && in_x1) ? __ldg(q + 1) : CUDART_NAN_F;
+            pres[dz][dy] = __ballot_sync(kFull, a == a && n == n);
+            posm[dz][dy] = __ballot_sync(kFull, a > kTiny && a < kHuge && n > kTiny && n < kHuge);
+            negm[dz][dy] = __ballot_sync(kFull, a < -kTiny && a > -kHuge && n < -kTiny && n > -kHuge);
         }
     unsigned any_pos = 0u, any_neg = 0u, any_mix = 0u;
+    const unsigned v00 = (unsigned)chunk * (unsigned)vpc + ((unsigned)z0 * (unsigned)dimy + (unsigned)y0) * (unsigned)wpr + (unsigned)xw;
 #pragma unroll
     for (int dz = 0; dz < 4; dz++)
 #pragma unroll
@@ -147,7 +138,7 @@ __global__ void __launch_bounds__(128) cell_class_kernel(const float *__restrict
             const unsigned vn = negm[dz][dy] & negm[dz][dy + 1] & negm[dz + 1][dy] & negm[dz + 1][dy + 1];
             any_pos |= vp; any_neg |= vn; any_mix |= v & ~vp & ~vn;
             if (lane == 0 && y < dimy && z < dimz)
-                vbits[(size_t)chunk * vpc + ((size_t)z * dimy + y) * wpr + xw] = make_uint2(v & ~vn, v & ~vp);
+                vbits[v00 + ((unsigned)dz * (unsigned)dimy + (unsigned)dy) * (unsigned)wpr] = make_uint2(v & ~vn, v & ~vp);
         }
     if (lane < 8) {  // one block per lane: region bits 1 = holds a positive cell, 2 = negative, 4 = mixed
         const int bx = xw * 8 + lane;
