@@ -85,7 +85,7 @@ typedef struct spsg_loss_targets {
 } spsg_loss_targets;
 
 /* Optional argument of the indexed / fused forwards: the gradient buffers the matching backward will write.  When
- * given, the forward's fill pass also clears their rows [0, N) (same launch, coalesced 16-byte stores), and the
+ * given, the forward also clears their rows [0, N) (16-byte stores by the raycast kernel's own warps), and the
  * backward -- called with SPSG_FLAG_GRADS_CLEARED -- is a single gather launch that only touches voxels that received
  * pixels.  Pass NULL when no backward will follow (the backward then clears the rows itself, like the reference's
  * memsets at raycast_rgbd_cuda_kernel.cu:557-560). */
