@@ -309,6 +309,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                             const int want = max(1, min(__float2int_rd((tin - margin - ray) * inv_inc) - 1, jump_cap));
                             ray = step_advance(s_steps, a.inc, ray, want);
                         }
+                        // The samples between there and the first one with floor(p) in [0, dim - 1) on every axis are
+                        // invalid (see the march) and the march state is still "no valid sample": step over them here,
+                        // one real add each, instead of spending a warp iteration on each of them.
+                        for (int k = 0; k < 6 && ray < t_end; k++) {
+                            const int ix = __float2int_rd(__fmaf_rn(r.dx, ray, r.camx)), iy = __float2int_rd(__fmaf_rn(r.dy, ray, r.camy)),
+                                      iz = __float2int_rd(__fmaf_rn(r.dz, ray, r.camz));
+                            if ((unsigned)ix < (unsigned)a.vx && (unsigned)iy < (unsigned)a.vy && (unsigned)iz < (unsigned)a.vz) break;
+                            if (!skip_ok) break;
+                            ray = __fadd_rn(ray, a.inc);
+                        }
                     }
                 }
                 q.r = r; q.invx = invx; q.invy = invy; q.invz = invz; q.kx = kx; q.ky = ky; q.kz = kz;
