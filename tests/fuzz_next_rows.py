@@ -78,5 +78,36 @@ for c in range(cases):
             fin = torch.isfinite(gb)
             if not torch.allclose(ga[fin], gb[fin], rtol=1e-4, atol=1e-7):
                 fail(c, "losses_2d grad %s max err %g" % (name, float((ga[fin] - gb[fin]).abs().max()))); break
+    # ---- per-voxel normals (loss.py:285-306)
+    if locs.shape[0] > 0 and min(dz, dy, dx) >= 3 and int(locs[-1, 3]) == B - 1:
+        vals_sdf = (torch.randn(locs.shape[0], 1, generator=g) * 1.5).to(dev)
+        tr = None
+        if rng.random() < 0.7:
+            q, _ = np.linalg.qr(rng.standard_normal((B, 3, 3)))
+            m = np.tile(np.eye(4, dtype=np.float32), (B, 1, 1)); m[:, :3, :3] = q; m[:, :3, 3] = rng.standard_normal((B, 3))
+            tr = torch.from_numpy(m.astype(np.float32)).to(dev)
+        wn = torch.randn(locs.shape[0], 3, generator=g).to(dev)
+        a = vals_sdf.clone().requires_grad_(True); b2 = vals_sdf.clone().requires_grad_(True)
+        want_n = R.compute_normals_sparse(locs, a, (dz, dy, dx), tr)
+        got_n = compute_normals_sparse(locs, b2, (dz, dy, dx), tr, num_chunks=B)
+        (want_n * wn).sum().backward(); (got_n * wn).sum().backward()
+        scale = float(a.grad.abs().max()) + 1e-12
+        if float((got_n - want_n).abs().max()) > 1e-5 or float((b2.grad - a.grad).abs().max()) > 1e-4 * scale:
+            # ill-conditioned voxels (|gradient of the sdf| near the normalisation eps) amplify fp32 rounding: judge both
+            # against the same expression in float64
+            a64 = vals_sdf.double().clone().requires_grad_(True)
+            n64 = R.compute_normals_sparse(locs, a64, (dz, dy, dx), None if tr is None else tr.double())
+            (n64 * wn.double()).sum().backward()
+            e_mine = float((b2.grad.double() - a64.grad).abs().max()); e_lit = float((a.grad.double() - a64.grad).abs().max())
+            # (a voxel whose sdf gradient is tiny and axis-aligned has an exactly-zero true component that fp32 turns into
+            #  |q| * ulp / |g|: accepted up to 1e-3 of the largest gradient entry, the bar of the atomically accumulated grads)
+            if e_mine > max(4.0 * e_lit, 1e-3 * scale, 1e-5):
+                err = (b2.grad.double() - a64.grad).abs()[:, 0]
+                top = torch.topk(err, min(3, err.numel()))[1]
+                for j in top.tolist():
+                    print("   voxel %d loc %s dims %s mine %.9g literal %.9g f64 %.9g  tr %s" % (
+                        j, locs[j].tolist(), (dz, dy, dx), float(b2.grad[j]), float(a.grad[j]), float(a64.grad[j]), tr is not None), flush=True)
+                fail(c, "normals: value err %g grad err %g (scale %g); vs float64: mine %g literal %g" % (
+                    float((got_n - want_n).abs().max()), float((b2.grad - a.grad).abs().max()), scale, e_mine, e_lit))
 print("%d cases, %d mismatching, %.1f s" % (cases, bad, time.time() - t0))
 sys.exit(1 if bad else 0)
