@@ -59,7 +59,7 @@ extern "C" SPSG_API int spsg_labels_from_render(const float *semantic, int64_t n
     if (reinterpret_cast<uintptr_t>(semantic) & 7u) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "semantic must be 8-byte aligned");
     if (hist) SPSG_CUDA_TRY(cudaMemsetAsync(hist, 0, (kClasses + 1) * sizeof(int64_t), st));
     if (num_pixels == 0) return SPSG_OK;
-    const unsigned grid = (unsigned)std::min<long long>((num_pixels + 255) / 256, 148ll * 8);
+    const unsigned grid = (unsigned)std::min<long long>((num_pixels + 255) / 256, (long long)spsg_internal_sm_count() * 8);
     labels_kernel<<<grid, 256, 0, st>>>(semantic, num_pixels, labels, reinterpret_cast<unsigned long long *>(hist));
     SPSG_CUDA_TRY(cudaGetLastError());
     return SPSG_OK;

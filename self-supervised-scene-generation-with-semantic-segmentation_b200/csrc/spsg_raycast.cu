@@ -315,6 +315,7 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
 // error plumbing for the other translation units of the library (csrc/spsg_internal.h)
 int spsg_internal_fail(int code, const char *msg) { return fail(code, msg); }
 int spsg_internal_fail_cuda(cudaError_t e, const char *where) { return fail_cuda(e, where); }
+int spsg_internal_sm_count() { return sm_count(); }
 
 extern "C" {
 

@@ -249,7 +249,7 @@ int launch_payload(bool scatter, const spsg_dense_payload *payloads, int count, 
             SPSG_CUDA_TRY(cudaMemsetAsync(payloads[p].dense, 0, cells * payloads[p].channels * sizeof(float), st));
     }
     if (num_locs == 0 || count == 0) return SPSG_OK;
-    const unsigned grid = (unsigned)std::min<long long>((num_locs + 255) / 256, 148ll * 16);
+    const unsigned grid = (unsigned)std::min<long long>((num_locs + 255) / 256, (long long)spsg_internal_sm_count() * 16);
     if (scatter) dense_payload_kernel<true><<<grid, 256, 0, st>>>(a, reinterpret_cast<const longlong4 *>(locs), num_locs, dimz, dimy, dimx);
     else dense_payload_kernel<false><<<grid, 256, 0, st>>>(a, reinterpret_cast<const longlong4 *>(locs), num_locs, dimz, dimy, dimx);
     SPSG_CUDA_TRY(cudaGetLastError());
