@@ -194,7 +194,51 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
     const int tiles_per_image = blocks_x * blocks_y * 4;
     const int total_tiles = tiles_per_image * a.views;
 
-    for (int chunk = blockIdx.x % a.num_chunks; chunk < a.num_chunks; chunk += gridDim.x) {
+    // Chunks of this CTA: its own first (chunk i % B, then + gridDim, ...), then -- work stealing for ragged batches --
+    // any other chunk that still has unclaimed tiles in its dynamic counter.  Warp 0 picks, the CTA follows.
+    __shared__ int s_next_chunk;
+    int own_next = blockIdx.x % a.num_chunks, steal_k = 0;
+    for (bool first_chunk = true;; first_chunk = false) {
+        if (own_next >= a.num_chunks && a.num_chunks == 1) break;  // a single chunk: nothing to steal
+        if (!first_chunk) {
+            __syncthreads();  // all warps are done reading the maps before the next chunk's copy overwrites them
+            if (kSmemMaps) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        int code = -1;
+        if (own_next < a.num_chunks) {
+            code = own_next * 2 + 1;  // (every thread knows: no election)
+        } else {
+            if (warp == 0) {
+                // candidates (blockIdx + k) % B, k = steal_k + 1 ..., 32 at a time: every lane looks at one counter
+                int pick = -1;
+                while (pick < 0 && steal_k + 1 < a.num_chunks) {
+                    const int k = steal_k + 1 + lane;
+                    bool open = false;
+                    int cand = 0;
+                    if (k < a.num_chunks) {
+                        cand = (int)((blockIdx.x + (unsigned)k) % (unsigned)a.num_chunks);
+                        const int owners = cand < (int)gridDim.x ? ((int)gridDim.x - 1 - cand) / a.num_chunks + 1 : 1;
+                        const int fixed = min(total_tiles, owners * kWarps);  // tiles dealt statically to the chunk's owners
+                        open = fixed + *reinterpret_cast<volatile int32_t *>(a.tile_counter + cand) < total_tiles;
+                    }
+                    const unsigned m = __ballot_sync(kFull, open);
+                    if (m) {
+                        const int src = __ffs(m) - 1;
+                        pick = __shfl_sync(kFull, cand, src) * 2;
+                        steal_k += src + 1;
+                    } else {
+                        steal_k += 32;
+                    }
+                }
+                if (lane == 0) s_next_chunk = pick;
+            }
+            __syncthreads();
+            code = s_next_chunk;
+        }
+        if (code < 0) break;
+        const int chunk = code >> 1;
+        const bool own = (code & 1) != 0;
+        if (own) own_next += (int)gridDim.x;
         if (kSmemMaps) {
             if (threadIdx.x == 0) {  // cell classes + block map: TMA bulk copies, completion on the mbarrier
                 const unsigned vb_bytes = (unsigned)(a.vpc * sizeof(uint2)), bm_bytes = (unsigned)a.bpc;
@@ -217,10 +261,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
 
         // CTAs that share this chunk: ranks 0..group-1.  First round static and contiguous per CTA, then dynamic.
         const int nb = a.num_chunks;
-        const int group = ((int)gridDim.x - 1 - (int)(blockIdx.x % nb)) / nb + 1, rank = blockIdx.x / nb;
+        const int group = chunk < (int)gridDim.x ? ((int)gridDim.x - 1 - chunk) / nb + 1 : 1, rank = blockIdx.x / nb;
         const int static_tiles = min(total_tiles, group * kWarps);
         const int per = static_tiles / group, extra = static_tiles - per * group;
-        const int my_first = rank * per + min(rank, extra), my_count = per + (rank < extra ? 1 : 0);
+        const int my_first = rank * per + min(rank, extra), my_count = own ? per + (rank < extra ? 1 : 0) : 0;
         int tile = warp < my_count ? my_first + warp : total_tiles;
         int32_t *counter = a.tile_counter + chunk;
         if (tile >= total_tiles && static_tiles < total_tiles) {
@@ -680,13 +724,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
             tile = __shfl_sync(kFull, next, 0);
             if (tile < total_tiles) prepare(tile, q);
         }
-        if (kSmemMaps) {
-            phase ^= 1u;
-            if (chunk + (int)gridDim.x < a.num_chunks) {
-                __syncthreads();  // all warps are done reading the maps before the next chunk's copy overwrites them
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            }
-        }
+        if (kSmemMaps) phase ^= 1u;
     }
 }
 
