@@ -314,7 +314,7 @@ def roofline_ours(ctx, dev, steps):
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed ncu --set full captures
     # (profiles/r01_c2_ncu_full_summary.md, r01_c3_ncu_full_summary.md); in C2 the 6.9 MB of images are still dirty
     # in the 126 MB L2 when the kernel ends, so only the reads show up
-    traffic = {1: 2.84e6, 40: 397.4e6}.get(ctx["rays"] // (ctx["S"].WIDTH * ctx["S"].HEIGHT))
+    traffic = {1: 2.52e6, 40: 397.4e6}.get(ctx["rays"] // (ctx["S"].WIDTH * ctx["S"].HEIGHT))
     return {"bound": "hbm", "kernel": "raycast_forward_kernel", "achieved": round(achieved, 1), "peak": peak,
             "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": which,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": round(us, 2),
