@@ -15,6 +15,9 @@ rc = RaycastRGBD(B, chunk_dims, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.T
 view_np, intr_np = R.window_views(F, chunk_dims)
 view = torch.from_numpy(np.tile(view_np, (B, 1, 1))).to(dev); intr = torch.from_numpy(np.tile(intr_np, (B, 1))).to(dev)
 grid2cam = torch.inverse(view[::F]).contiguous()
+import sys as _s
+if '--prepared' in _s.argv:
+    predict.prepare_groups([windows[s:s + B] for s in range(0, len(windows), B)], (64, 64))
 T = {}
 def tick(name, t0):
     torch.cuda.synchronize(); t1 = time.perf_counter(); T[name] = T.get(name, 0) + t1 - t0; return t1
@@ -24,23 +27,10 @@ for rep in range(3):
         group = windows[s:s + B]
         torch.cuda.synchronize(); t = time.perf_counter()
         locs, sdf, color, sem = predict.predict_group(group, (64, 64)); t = tick('predict_group', t)
-        counts = torch.bincount(locs[:, 3], minlength=len(group)).tolist(); t = tick('counts', t)
+        edges = torch.searchsorted(locs[:, 3].contiguous(), torch.arange(len(group) + 1, device=dev)).tolist(); t = tick('counts', t)
         with torch.no_grad():
             normals = compute_normals_sparse(locs, sdf, chunk_dims, grid2cam, num_chunks=B); t = tick('normals', t)
             _, depth, _, sem_img = rc(locs, sdf, color, normals, sem, view, intr); t = tick('raycast', t)
-            labels = R.labels_from_render_logits(sem_img, depth); t = tick('labels', t)
-            h = torch.bincount(labels.reshape(-1).long(), minlength=15).to(torch.float64); t = tick('hist', t)
+            from spsg_b200.losses import labels_from_render
+            labels, h = labels_from_render(sem_img, histogram=True); t = tick('labels+hist', t)
 print({k: round(v * 1e3, 2) for k, v in T.items()}, 'ms per room; total', round(sum(T.values()) * 1e3, 2))
-# inside predict_group
-T.clear()
-for s in range(0, len(windows), B):
-    group = windows[s:s + B]
-    torch.cuda.synchronize(); t = time.perf_counter()
-    head = torch.full((len(group), 1, 128, 64, 64), 7.0, device=dev)
-    for b, (y0, x0) in enumerate(group):
-        win = room[:, y0:y0 + 64, x0:x0 + 64]; head[b, 0, :, :win.shape[1], :win.shape[2]] = win
-    t = tick('assemble', t)
-    locs, vals = sparsify.sparsify_predictions(head, 3.0); t = tick('sparsify', t)
-    origin = torch.tensor(group, dtype=torch.int64, device=dev)
-    c, sm = R._payload_from_positions(locs[:, 0], locs[:, 1] + origin[locs[:, 3], 0], locs[:, 2] + origin[locs[:, 3], 1], 0); t = tick('payload', t)
-print({k: round(v * 1e3, 2) for k, v in T.items()})
