@@ -133,8 +133,9 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCo
 // The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
 // warp per item.  Lane k fetches the k-th registered pixel id (one coalesced load) and that pixel's 21 upstream
 // gradients (independent 8- and 4-byte loads), parks them in shared memory, and lane c then adds column c in
-// registration order as grad / count (kernel.cu:398-418) -- a fixed order, so with one view per chunk the result is
-// deterministic and written with plain stores.  With several views per chunk the per-view means of a voxel are summed
+// registration order as grad / count (kernel.cu:398-418); with one view per chunk the result is written with plain
+// stores, no float atomics (the registration order itself depends on which warp's atomic reached a voxel first, so two
+// runs can differ in the last bit).  With several views per chunk the per-view means of a voxel are summed
 // with float atomics onto rows the zero kernel cleared (kAtomic).
 constexpr int kGatherWarps = 8;
 

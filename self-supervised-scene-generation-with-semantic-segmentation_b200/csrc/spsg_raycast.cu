@@ -17,7 +17,7 @@
 //   * the regula-falsi refinement is deferred until every lane of the warp has found its crossing;
 //   * rendered pixels are staged in shared memory and written with coalesced 128-bit stores;
 //   * the forward appends every (voxel, view) pair that received a pixel to a list, so the backward is one launch:
-//     a deterministic per-voxel gather over that list (no float atomics for one view per chunk, no 524288-block
+//     a per-voxel gather over that list (no float atomics for one view per chunk, no 524288-block
 //     launch, no 164 MB memsets), optionally fused with the 2D losses.
 #include <cuda_runtime.h>
 #include <math_constants.h>
