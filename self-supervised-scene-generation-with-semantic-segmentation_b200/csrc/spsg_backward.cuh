@@ -133,9 +133,9 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCo
 // The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
 // warp per item.  Lane k fetches the k-th registered pixel id (one coalesced load) and that pixel's 21 upstream
 // gradients (independent 8- and 4-byte loads), parks them in shared memory, and lane c then adds column c in
-// registration order as grad / count (kernel.cu:398-418); with one view per chunk the result is written with plain
-// stores, no float atomics (the registration order itself depends on which warp's atomic reached a voxel first, so two
-// runs can differ in the last bit).  With several views per chunk the per-view means of a voxel are summed
+// registration order (kernel.cu:398-418: mean = sum / count), accumulating in double precision: the registration order
+// depends on which warp's atomic reached a voxel first, and a double sum rounded once gives the same fp32 mean for every
+// order (up to an exact tie).  With one view per chunk the result is written with plain stores, no float atomics.  With several views per chunk the per-view means of a voxel are summed
 // with float atomics onto rows the zero kernel cleared (kAtomic).
 constexpr int kGatherWarps = 8;
 
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
         const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
         const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
         const float inv = __frcp_rn((float)max(cnt, 1));
-        float acc0 = 0.0f, acc1 = 0.0f;  // channels hl and 16 + hl
+        double acc0 = 0.0, acc1 = 0.0;  // channels hl and 16 + hl; double: the sum does not depend on the pixel order to fp32 precision
         for (int k0 = 0; k0 < cnt; k0 += 16) {
             const int m = min(16, cnt - k0);
             if (hl < m) {
@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
             }
             __syncwarp(hmask);
             for (int r = 0; r < m; r++) {
-                acc0 = __fmaf_rn(tile[r * 21 + hl], inv, acc0);
-                if (hl < 5) acc1 = __fmaf_rn(tile[r * 21 + 16 + hl], inv, acc1);
+                acc0 += (double)tile[r * 21 + hl];
+                if (hl < 5) acc1 += (double)tile[r * 21 + 16 + hl];
             }
             __syncwarp(hmask);
         }
@@ -189,12 +189,13 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
         if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
         else if (hl == 1) d1 = a.d_depth + idx;
         else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
+        const float m0 = (float)(acc0 * (double)inv), m1 = (float)(acc1 * (double)inv);  // mean = sum / count (kernel.cu:398-418)
         if (kAtomic) {
-            atomicAdd(d0, acc0);
-            if (d1) atomicAdd(d1, acc1);
+            atomicAdd(d0, m0);
+            if (d1) atomicAdd(d1, m1);
         } else {
-            *d0 = acc0;
-            if (d1) *d1 = acc1;
+            *d0 = m0;
+            if (d1) *d1 = m1;
         }
         item = next_item;
     }
