@@ -361,3 +361,27 @@ def test_oversize_input_is_truncated_like_the_reference_wrapper(cuda_device, cap
     _assert_render_equal(out_m, out_r, "truncated")
     assert torch.equal(mine.mapping3dto2d_num[:keep], ref.mapping3dto2d_num[:keep])
     assert (out_m[1] != NINF).any()
+
+
+def test_backward_reproduces_bit_for_bit(cuda_device):
+    """One view per chunk: repeated forward + backward passes give bit-identical voxel gradients although the order in which
+    warps register a voxel's pixels (the rows of mapping3dto2d) changes from run to run -- the gather sums in double."""
+    from spsg_b200 import synthetic as S
+    batch, t = scene_tensors([0, 1], cuda_device)
+    n = t["locs"].shape[0]
+    _, _, view, intr = views(2, 1, cuda_device, seed=0)
+    mine = _mine(cuda_device, 2, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, n)
+    grads, first = None, None
+    for rep in range(4):
+        leaves = [t[k].clone().requires_grad_(True) for k in ("sdf", "color", "normal", "semantic")]
+        out = mine(t["locs"], *leaves, view, intr)
+        if grads is None:
+            g = torch.Generator(device=cuda_device).manual_seed(1)
+            grads = [torch.randn(o.shape, device=cuda_device, generator=g) for o in out]
+        torch.autograd.backward(out, grads)
+        got = [bits(x.grad).clone() for x in leaves]
+        if first is None:
+            first = got
+        else:
+            for name, a, b in zip(("sdf", "color", "normal", "semantic"), first, got):
+                assert torch.equal(a, b), "%s gradient changed between runs" % name
