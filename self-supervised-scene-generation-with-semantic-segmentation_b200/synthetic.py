@@ -131,3 +131,57 @@ def make_targets(depth_render, color_render, label_render, seed=0, hole_fraction
     depth[rng.random(depth.shape) < hole_fraction] = 0.0
     color = np.where(np.isfinite(color_render), color_render, 0.5).astype(np.float32)
     return depth, color, label_render.astype(np.uint8)
+
+
+def make_train_sample(seeds, views_per_chunk=1, dims_zyx=DIMS_ZYX, width=WIDTH, height=HEIGHT, view_seed=0, view_kw=None):
+    """One synthetic training batch with the keys of the reference dataloader's samples (scene_dataloader.py /
+    data_util.py:862-902; train.py:413-445), as numpy arrays: the target chunk (dense truncated SDF, uint8 colours, per-voxel
+    labels 0..14), an incomplete input scan of it (a box-shaped region is missing), the colour-inpainting mask, and
+    `views_per_chunk` frames per chunk (colour in [0,1], depth in metres with 5 % holes, camera->grid matrices, intrinsics).
+
+        input (B,4,Dz,Dy,Dx) f32 [sdf, r, g, b]   mask (B,1,Dz,Dy,Dx) f32   sdf (B,1,Dz,Dy,Dx) f32   known (B,1,Dz,Dy,Dx) bool
+        colors (B,Dz,Dy,Dx,3) u8   semantics (B,1,Dz,Dy,Dx) i64   images_color (I,3,H,W) f32   images_depth (I,H,W) f32
+        view_matrix (I,4,4) f32   images_intrinsic (I,4) f32
+    """
+    B = len(seeds)
+    dz, dy, dx = dims_zyx
+    out = {k: [] for k in ("input", "mask", "sdf", "known", "colors", "semantics")}
+    for s in seeds:
+        sdf, prim = sdf_volume(s, dims_zyx)
+        rng = np.random.default_rng(7000003 * (s + 1))
+        band = np.abs(sdf) < TRUNCATION
+        colors = np.zeros(dims_zyx + (3,), dtype=np.uint8)
+        colors[band] = rng.integers(1, 256, size=(int(band.sum()), 3), dtype=np.uint8)
+        label = np.full(dims_zyx, NUM_CLASSES, dtype=np.int64)
+        z = np.arange(dz)[:, None, None]
+        label[band] = ((prim * 3 + z // 16) % NUM_CLASSES)[band]
+        label[band & (rng.random(dims_zyx) < 0.05)] = NUM_CLASSES
+        # the scan misses a box: no geometry, no colour there; the mask marks where colour has to be inpainted
+        lo = np.array([dz // 4, dy // 4, dx // 4]) + rng.integers(0, 8, 3)
+        hi = lo + np.array([dz // 3, dy // 3, dx // 3])
+        hole = np.zeros(dims_zyx, dtype=bool)
+        hole[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = True
+        in_sdf = np.where(hole, np.float32(TRUNCATION), sdf).astype(np.float32)
+        in_col = np.where(hole[..., None], 0.0, colors.astype(np.float32) / 255.0).astype(np.float32)
+        out["input"].append(np.concatenate([in_sdf[None], in_col.transpose(3, 0, 1, 2)], 0))
+        out["mask"].append(hole[None].astype(np.float32))
+        out["sdf"].append(sdf[None].astype(np.float32))
+        out["known"].append(np.ones((1,) + dims_zyx, dtype=bool))
+        out["colors"].append(colors)
+        out["semantics"].append(label[None])
+    sample = {k: np.stack(v) for k, v in out.items()}
+    images = B * views_per_chunk
+    view, intr = make_views(B, views_per_chunk, seed=view_seed, **(view_kw or {}))
+    intr = intr.copy()
+    intr[:, 0] *= width / WIDTH
+    intr[:, 2] = (intr[:, 2] + 0.5) * width / WIDTH - 0.5
+    intr[:, 1] *= height / HEIGHT
+    intr[:, 3] = (intr[:, 3] + 0.5) * height / HEIGHT - 0.5
+    rng = np.random.default_rng(31 + view_seed + 1009 * (seeds[0] if seeds else 0))
+    sample["images_color"] = rng.random((images, 3, height, width), dtype=np.float32)
+    depth = rng.uniform(0.8, 1.6, (images, height, width)).astype(np.float32)
+    depth[rng.random((images, height, width)) < 0.05] = 0.0
+    sample["images_depth"] = depth
+    sample["view_matrix"] = view.astype(np.float32)
+    sample["images_intrinsic"] = intr.astype(np.float32)
+    return sample

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "self-supervised-scene-generation-with-semantic-segmentation_b200", "lib", "libspsg_raycast.so")
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+cubin = [os.path.join(tmp, f) for f in sorted(os.listdir(tmp)) if f.endswith(".cubin") and f.startswith("spsg_raycast.")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 lines, cur, infn, inl = [], None, False, ""
 for l in dis.splitlines():
