@@ -1,29 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- raycast fwd+bwd rays/s on BASELINE.json's config.
+"""bench.py -- BASELINE.json's metric: raycast fwd+bwd rays/s, % of the HBM roofline, train chunks/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5]
 
-A "step" is one forward + backward pass of the hot path over one batch of synthetic input:
-  c2 (default, BASELINE configs[1])  one 64x64x128 chunk, one 320x256 view, depth/colour/normal/semantic outputs
-  c3 (BASELINE configs[2])           8 chunks x 5 views (40 images, 3 276 800 rays)
-`value`   rays/s with every input already resident in HBM, the step replayed from a CUDA graph (no host launch
-          latency in the device number); 4+ distinct input sets are rotated so that consecutive steps never find
-          their data in the 126 MB L2.
-`e2e`     the same metric through the public Python API (RaycastRGBD + fused 2D losses for ours; the reference
-          wrapper's call order + its literal PyTorch losses for --impl reference) with HOST buffers: every step
-          copies its voxel tensors, cameras and target frames from pinned host memory and reads the loss back.
+A "step" is one pass of the hot path over one batch of synthetic input:
+  c3 (default, BASELINE configs[2])  8 chunks 64x64x128 x 5 views 320x256 (3 276 800 rays): raycast forward with the depth /
+                                     colour / 2D-semantic losses fused in, and its backward (voxel gradients)
+  c2 (BASELINE configs[1])           one chunk, one view; also reported inside the default line as `c2`
+  c5 (BASELINE configs[4])           whole-room 2 cm inference by sliding chunks with multi-view semantic rendering
+`value`   rays/s with every input already resident in HBM, the step replayed from a CUDA graph (no host launch latency in
+          the device number); distinct input sets are rotated so that consecutive steps never find their data in the
+          126 MB L2; the timed region is at least MIN_REGION_S long whatever --steps says.
+`e2e`     the same metric through the public Python API with HOST buffers: every step copies its voxel tensors, cameras
+          and target frames from pinned host memory (copy stream, double-buffered) and reads the loss back.
 `roofline`     the dominant kernel (raycast forward) timed with CUDA events on its launch stream (C-ABI timing hook),
-               algorithmic bytes 116*Nv + 84*Np per launch over MEASURED_PEAKS.json's HBM copy peak.
-`cpu_baseline` the scalar C restatement of the same raycast (oracle/, OpenMP over pixels) on the box's host cores.
---impl reference  runs the UNMODIFIED reference extension (oracle/_ref, built from /root/reference where it lies)
-          on the same GPU through its own native entry points in its wrapper's order; the reference has no CPU
-          implementation of this path, so its arm is its CUDA extension (falls back to the CPU port if the
-          extension is not present on the box).
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); units are independent chunk x view batches, so
-ranks shard them with no data-path collective ("scaling": "weak"); time is the max over ranks.
+               algorithmic bytes per launch over MEASURED_PEAKS.json's HBM copy peak.
+`train`        BASELINE configs[3]: the train.py step (reference generator fwd/bwd + 3D losses + three raycasts + 2D losses +
+               Adam) on this package's ops, DistributedDataParallel over the ranks (NCCL gradient all-reduce), chunks/s.
+`cpu_baseline` the scalar C restatement of the raycast (oracle/, OpenMP over pixels) and BASELINE configs[0] (reference
+               generator forward + class-weighted 3D cross-entropy, PyTorch CPU) on the box's host cores.
+--impl reference  runs the UNMODIFIED reference: its wrapper (baseline/_ref/.../raycast_rgbd.py) on its CUDA extension
+          (oracle/_ref, built from /root/reference where it lies), one view per call as it renders, and its literal
+          PyTorch losses; same workload, copy protocol and timing rules.  The reference has no CPU implementation of this
+          path, so its arm is its CUDA extension (falls back to the CPU port if the extension is not on the box).
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); units are independent chunk x view batches, so ranks shard
+them with no data-path collective ("scaling": "weak"); time is the max over ranks.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -38,19 +43,23 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-MAX_LOCS = 640000  # train.py:136 max_num_locs_per_sample (sizes the reference's memsets)
-E2E_REPEATS = 3   # timed regions of the end-to-end leg (median reported)
+MAX_LOCS = 640000      # train.py:136 max_num_locs_per_sample (sizes the reference's memsets)
+E2E_REPEATS = 3        # timed regions of the end-to-end leg (median reported), both arms
+MIN_REGION_S = 0.5     # the device-resident timed region lasts at least this long
+TRAIN_BATCH = 8        # chunks per GPU and step of the train leg (BASELINE configs[2]/[3])
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c5"])
     ap.add_argument("--sets", type=int, default=0, help="distinct resident input sets to rotate (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step leg (configs[3])")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the c2 / un-fused secondary numbers")
     return ap.parse_args()
 
 
@@ -85,6 +94,13 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------------------------------
+
+H2D_KEYS = ("locs", "sdf", "color", "normal", "semantic", "view", "intr", "t_depth", "t_color", "t_label")
+
+
 def make_host_sets(num_sets, B, F, rank):
     """Seeded synthetic chunk batches + cameras + target frames, as pinned host tensors."""
     from spsg_b200 import synthetic as S
@@ -114,32 +130,112 @@ def bytes_of(d, keys):
     return int(sum(d[k].numel() * d[k].element_size() for k in keys))
 
 
-H2D_KEYS = ("locs", "sdf", "color", "normal", "semantic", "view", "intr", "t_depth", "t_color", "t_label")
+def auto_sets(B, F):
+    per_set_mb = 45.0 * B + 14.0 * B * F
+    return max(2, int(math.ceil(190.0 / per_set_mb))), per_set_mb
 
 
-def run_ours(args, dev, rank, B, F, num_sets):
-    from spsg_b200 import _native as N
-    from spsg_b200 import synthetic as S
-    from spsg_b200.losses import render_with_2d_losses
-    from spsg_b200.raycast_rgbd import RaycastRGBD
-    host = make_host_sets(num_sets, B, F, rank)
-    rays = B * F * S.WIDTH * S.HEIGHT
-    devsets, mods, grads = [], [], []
-    for h in host:
-        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        devsets.append(d)
-        mods.append(RaycastRGBD(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST,
-                                S.RAY_INCREMENT, max_num_frames=F, max_num_locs_per_sample=MAX_LOCS, device=dev))
-        g = torch.Generator(device=dev).manual_seed(5)
-        grads.append([torch.randn(s, device=dev, generator=g) for s in
-                      ((B * F, S.HEIGHT, S.WIDTH, 3), (B * F, S.HEIGHT, S.WIDTH), (B * F, S.HEIGHT, S.WIDTH, 3),
-                       (B * F, S.HEIGHT, S.WIDTH, 14))])
-    nv = int(np.mean([d["locs"].shape[0] for d in devsets]))
-    cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
-    from spsg_b200 import raycast_rgbd_cuda as rc
+def reduce_max_ms(ms, dev, world):
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
-    def step_resident(i):
-        d, m, g = devsets[i % num_sets], mods[i % num_sets], grads[i % num_sets]
+
+def timed_replays(graph, replays, dev, world):
+    """`replays` graph launches bracketed by barrier + synchronize, CUDA-event time, max over ranks."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    ms = reduce_max_ms(a.elapsed_time(b), dev, world)
+    if world > 1:
+        dist.barrier()
+    return ms
+
+
+def capture_rotation(step, num_sets, dev, warmup):
+    """Warm up, then capture one rotation over all input sets into a CUDA graph."""
+    for i in range(max(warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step(0)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(num_sets):
+                step(i)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    return graph
+
+
+def measure_resident(step, num_sets, dev, world, want_steps, warmup):
+    """(ms, steps) of a device-resident loop: graph replays covering >= want_steps steps and >= MIN_REGION_S."""
+    graph = capture_rotation(step, num_sets, dev, warmup)
+    probe = timed_replays(graph, 2, dev, world) / 2.0  # ms per rotation
+    replays = max(1, int(math.ceil(want_steps / num_sets)), int(math.ceil(MIN_REGION_S * 1e3 / max(probe, 1e-3))))
+    ms = timed_replays(graph, replays, dev, world)
+    return ms, replays * num_sets, graph
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------------------------------
+
+class Ours:
+    def __init__(self, dev, rank, B, F, num_sets):
+        from spsg_b200 import _native as N
+        from spsg_b200 import raycast_rgbd_cuda as rc
+        from spsg_b200 import synthetic as S
+        from spsg_b200.losses import render_loss_and_voxel_grads, render_with_2d_losses
+        from spsg_b200.raycast_rgbd import RaycastRGBD
+        self.N, self.rc, self.S, self.render, self.render_pair = N, rc, S, render_with_2d_losses, render_loss_and_voxel_grads
+        self.dev, self.B, self.F, self.num_sets = dev, B, F, num_sets
+        self.host = make_host_sets(num_sets, B, F, rank)
+        self.rays = B * F * S.WIDTH * S.HEIGHT
+        self.devsets, self.mods, self.grads = [], [], []
+        for h in self.host:
+            d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+            self.devsets.append(d)
+            self.mods.append(RaycastRGBD(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST,
+                                         S.RAY_INCREMENT, max_num_frames=F, max_num_locs_per_sample=MAX_LOCS, device=dev))
+            g = torch.Generator(device=dev).manual_seed(5)
+            self.grads.append([torch.randn(s, device=dev, generator=g) for s in
+                               ((B * F, S.HEIGHT, S.WIDTH, 3), (B * F, S.HEIGHT, S.WIDTH), (B * F, S.HEIGHT, S.WIDTH, 3),
+                                (B * F, S.HEIGHT, S.WIDTH, 14))])
+        self.nv = int(np.mean([d["locs"].shape[0] for d in self.devsets]))
+        self.cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
+        self.loss_sink = torch.zeros((), device=dev)
+
+    def step_fused(self, i):
+        """forward with the three 2D losses fused in + backward from the scalar loss (the north-star path)."""
+        S = self.S
+        k = i % self.num_sets
+        d, m = self.devsets[k], self.mods[k]
+        # the two native calls of spsg_b200.losses (spsg_raycast_forward_loss + spsg_raycast_backward_loss) without the
+        # autograd wrapper: voxel gradients land in the module's d_* rows, the loss in loss_out[3]
+        loss_out, _ = self.render_pair(m, d["locs"], d["sdf"], d["color"], d["normal"], d["semantic"], d["view"], d["intr"],
+                                       images_depth=d["t_depth"], images_color=d["t_color"], target2d_label=d["t_label"],
+                                       weight_semantic_class=self.cw, voxelsize=S.VOXELSIZE)
+        self.loss_sink.copy_(loss_out[3])
+
+    def step_unfused(self, i):
+        """forward + backward with upstream gradient images (the reference op boundary)."""
+        S, rc, B, F = self.S, self.rc, self.B, self.F
+        k = i % self.num_sets
+        d, m, g = self.devsets[k], self.mods[k], self.grads[k]
         n = d["locs"].shape[0]
         opts = [S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST, S.RAY_INCREMENT, 64, 64, 128]
         rc.forward(m.sparse_mapping, d["locs"], d["sdf"], d["color"], d["normal"], d["semantic"], d["view"],
@@ -150,128 +246,121 @@ def run_ours(args, dev, rank, B, F, num_sets):
                     [B, 64, 64, 128, n], m.d_color, m.d_depth, m.d_normal, m.d_semantic, views_per_chunk=F,
                     grads_cleared=True)
 
-    # ---- device-resident throughput: the rotation over all input sets captured once into a CUDA graph
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        step_resident(0)
-        side.synchronize()
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(num_sets):
-                step_resident(i)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    replays = max(1, (args.steps + num_sets - 1) // num_sets)
-    steps = replays * num_sets
-    for _ in range(max(1, args.warmup // num_sets)):
-        graph.replay()
-    torch.cuda.synchronize()
-    return dict(host=host, devsets=devsets, mods=mods, rays=rays, nv=nv, graph=graph, replays=replays, steps=steps,
-                cw=cw, step_resident=step_resident, render=render_with_2d_losses, N=N, S=S,
-                launches_per_step=5)  # fill, index, cell classes, forward, gather
+    def e2e(self, world, steps, warmup):
+        """End to end through the public API with HOST inputs: every step copies its voxel tensors, cameras and target
+        frames from pinned host memory (on a copy stream, double-buffered so that step i+1's copy overlaps step i's
+        kernels -- what a training loop's prefetcher does), renders + losses + backward, and reads the loss back."""
+        S, render, mods, host, cw, dev = self.S, self.render, self.mods, self.host, self.cw, self.dev
+        num_sets = len(host)
+        result = torch.zeros((), pin_memory=True)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        packed = [pack_host(h) for h in host]
+        cap = max(b.numel() for b, _ in packed)
+        slots = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
+        def issue_copy(i):
+            slot, (buf, _) = i % 2, packed[i % num_sets]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])  # the step that last used this slot is done with it
+                slots[slot][:buf.numel()].copy_(buf, non_blocking=True)
+                copied[slot].record(copy_stream)
 
-def timed_graph(ctx, dev, world):
-    """K steps from the graph, bracketed by barrier + synchronize, CUDA-event time, max over ranks."""
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(ctx["replays"]):
-        ctx["graph"].replay()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        ms = float(t.item())
-    return ms
+        view_cache = {}
 
+        def views(i):
+            key = (i % 2, i % num_sets)
+            if key not in view_cache:
+                view_cache[key] = slot_views(slots[key[0]], packed[key[1]][1])
+            return view_cache[key]
 
-def e2e_ours(ctx, dev, world, steps, warmup, mode="full"):
-    """End to end through the public API with HOST inputs: every step copies its voxel tensors, cameras and target
-    frames from pinned host memory (on a copy stream, double-buffered so that step i+1's copy overlaps step i's
-    kernels -- what a training loop's prefetcher does), renders + losses + backward, and reads the loss back."""
-    S, render, mods, host, cw = ctx["S"], ctx["render"], ctx["mods"], ctx["host"], ctx["cw"]
-    num_sets = len(host)
-    result = torch.zeros((), pin_memory=True)
-    copy_stream = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    # Every set is packed into ONE pinned host buffer (256-byte aligned fields, what a loader thread would hand over)
-    # and lands in one of two device-side slots with a single async copy; tensors are views into the slot.
-    def layout(h):
-        off, fields = 0, {}
-        for k in H2D_KEYS:
-            nbytes = h[k].numel() * h[k].element_size()
-            fields[k] = (off, nbytes, h[k].dtype, tuple(h[k].shape))
-            off += (nbytes + 255) // 256 * 256
-        return fields, off
-    packed = []
-    for h in host:
-        fields, total = layout(h)
-        buf = torch.empty(total, dtype=torch.uint8).pin_memory()
-        for k, (off, nbytes, dtype, shape) in fields.items():
-            buf[off:off + nbytes].view(dtype).view(shape).copy_(h[k])
-        packed.append((buf, fields))
-    cap = max(b.numel() for b, _ in packed)
-    slots = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    pick = (lambda i: i % 2) if mode == "compute" else (lambda i: i % num_sets)  # "compute": the slots keep sets 0/1
-
-    def issue_copy(i):
-        slot, (buf, _) = i % 2, packed[pick(i)]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])  # the step that last used this slot is done with it
-            slots[slot][:buf.numel()].copy_(buf, non_blocking=True)
-            copied[slot].record(copy_stream)
-
-    view_cache = {}
-
-    def views(i):
-        # tensor views into a slot depend on (slot, set layout) only: built once, like a loader's collate would
-        key = (i % 2, pick(i))
-        if key not in view_cache:
-            slot, (_, fields) = key[0], packed[key[1]]
-            view_cache[key] = {k: slots[slot][off:off + nbytes].view(dtype).view(shape)
-                               for k, (off, nbytes, dtype, shape) in fields.items()}
-        return view_cache[key]
-
-    def step(i, last):
-        slot, m = i % 2, mods[pick(i)]
-        if not last and mode != "compute":  # "copy" / "compute": tools/e2e_probe.py times the two halves alone
-            issue_copy(i + 1)
-        main.wait_event(copied[slot])
-        if mode == "copy":
-            consumed[slot].record(main)
-            return
-        d = views(i)
-        sdf = d["sdf"].detach().requires_grad_(True)  # fresh leaves every step
-        col = d["color"].detach().requires_grad_(True)
-        sem = d["semantic"].detach().requires_grad_(True)
-        total, terms, _ = render(m, d["locs"], sdf, col, d["normal"], sem, d["view"], d["intr"],
+        def step(i, last):
+            slot, m = i % 2, mods[i % num_sets]
+            if not last:
+                issue_copy(i + 1)
+            main.wait_event(copied[slot])
+            d = views(i)
+            sdf = d["sdf"].detach().requires_grad_(True)  # fresh leaves every step
+            col = d["color"].detach().requires_grad_(True)
+            sem = d["semantic"].detach().requires_grad_(True)
+            total, _, _ = render(m, d["locs"], sdf, col, d["normal"], sem, d["view"], d["intr"],
                                  images_depth=d["t_depth"], images_color=d["t_color"], target2d_label=d["t_label"],
                                  weight_semantic_class=cw, voxelsize=S.VOXELSIZE)
-        total.backward()
-        consumed[slot].record(main)
-        result.copy_(total.detach(), non_blocking=True)
+            total.backward()
+            consumed[slot].record(main)
+            result.copy_(total.detach(), non_blocking=True)
 
-    def run(n):
-        for e in consumed:
-            e.record(main)
-        issue_copy(0)
-        if mode == "compute":
-            issue_copy(1)
-        for i in range(n):
-            step(i, i == n - 1)
+        def run(n):
+            for e in consumed:
+                e.record(main)
+            issue_copy(0)
+            for i in range(n):
+                step(i, i == n - 1)
 
+        return e2e_protocol(run, steps, warmup, dev, world), float(result)
+
+    def roofline(self, steps, fused):
+        """Dominant kernel (raycast forward) alone: CUDA events around each launch on its stream, inputs rotated."""
+        N = self.N
+        N.timing_read(0), N.timing_read(1)
+        N.timing_enable(True)
+        for i in range(steps):
+            (self.step_fused if fused else self.step_unfused)(i)
+        torch.cuda.synchronize()
+        N.timing_enable(False)
+        f_ms, f_n = N.timing_read(0)
+        g_ms, g_n = N.timing_read(1)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        # forward: locs 32 B + payload 84 B per voxel in, 84 B per pixel out (+ 17 B of targets per pixel when fused)
+        alg_bytes = 116 * self.nv + (84 + (17 if fused else 0)) * self.rays
+        us = f_ms / max(f_n, 1) * 1e3
+        achieved = alg_bytes / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        traffic, traffic_src = ncu_traffic("c%d" % (3 if self.B * self.F > 1 else 2))
+        return {"bound": "hbm", "kernel": "raycast_forward_kernel" + ("<loss>" if fused else ""),
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": which,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": round(us, 2),
+                "backward_gather_us": round(g_ms / max(g_n, 1) * 1e3, 2),
+                "note": "not HBM-bound (traffic ~ algorithmic bytes): instruction issue / per-warp latency, see DESIGN.md "
+                        "section 5 and profiles/README.md"}
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the forward kernel per launch, from the committed `ncu --set full`
+    capture listed in profiles/ncu_traffic.json (written by tools/ncu_summary.py --traffic); None when there is none."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        entry = json.load(open(path))[workload]
+        return float(entry["dram_bytes_per_launch"]), "profiles/%s (%s)" % (entry["summary"], entry["kernel"])
+    except Exception:
+        return None, "no committed ncu capture for this workload"
+
+
+def pack_host(h):
+    """One pinned host buffer per input set (256-byte aligned fields, what a loader thread would hand over)."""
+    off, fields = 0, {}
+    for k in H2D_KEYS:
+        nbytes = h[k].numel() * h[k].element_size()
+        fields[k] = (off, nbytes, h[k].dtype, tuple(h[k].shape))
+        off += (nbytes + 255) // 256 * 256
+    buf = torch.empty(off, dtype=torch.uint8).pin_memory()
+    for k, (o, nbytes, dtype, shape) in fields.items():
+        buf[o:o + nbytes].view(dtype).view(shape).copy_(h[k])
+    return buf, fields
+
+
+def slot_views(slot, fields):
+    return {k: slot[off:off + nbytes].view(dtype).view(shape) for k, (off, nbytes, dtype, shape) in fields.items()}
+
+
+def e2e_protocol(run, steps, warmup, dev, world):
+    """Warm up, then the median of E2E_REPEATS timed regions of `steps` steps (max over ranks each)."""
     run(max(3, warmup))
     times = []
     for _ in range(E2E_REPEATS):  # host-side jitter is of the order of the step: median of a few timed regions
@@ -283,46 +372,84 @@ def e2e_ours(ctx, dev, world, steps, warmup, mode="full"):
         run(steps)
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        times.append(ms)
-    return float(np.median(times)), float(result)
+        times.append(reduce_max_ms(a.elapsed_time(b), dev, world))
+    return float(np.median(times))
 
 
-def roofline_ours(ctx, dev, steps):
-    """Dominant kernel (raycast forward) alone: CUDA events around each launch on its stream, inputs rotated."""
-    N = ctx["N"]
-    N.timing_read(0), N.timing_read(1)
-    N.timing_enable(True)
-    for i in range(steps):
-        ctx["step_resident"](i)
-    torch.cuda.synchronize()
-    N.timing_enable(False)
-    f_ms, f_n = N.timing_read(0)
-    g_ms, g_n = N.timing_read(1)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+# ---------------------------------------------------------------------------------------------------------------------
+# train step (BASELINE configs[3]) and CPU baselines
+# ---------------------------------------------------------------------------------------------------------------------
+
+def train_leg(impl, dev, rank, world, local, steps=8, warmup=3):
+    """chunks/s of the train.py step under DistributedDataParallel (one rank per GPU, NCCL all-reduce of the generator's
+    gradients); impl "ours" = spsg_b200.train_step on this package's ops, "reference" = the reference's loop body, wrapper,
+    losses and CUDA extension (baseline/ref_train_step.py)."""
+    from baseline import ref_loader
+    from spsg_b200 import synthetic as S
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref (reference model.py / loss.py) is not installed on this box"}
+    model_util = ref_loader.load_module("model")
+    loss_util = ref_loader.load_module("loss")
+    torch.backends.cudnn.benchmark = True  # train.py:122
+    torch.manual_seed(7)
+    sys.stdout, keep = open(os.devnull, "w"), sys.stdout  # the reference's Generator prints its parameter counts
+    try:
+        model = model_util.Generator(nf_in_geo=1, nf_in_color=4, nf=20, pass_geo_feats=True, truncation=S.TRUNCATION,
+                                     max_data_size=S.DIMS_ZYX).to(dev)  # train.py:153-156 defaults
+    finally:
+        sys.stdout = keep
+    model.train()
+    params = sum(p.numel() for p in model.parameters())
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=25)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)  # train.py:157
+    cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
+    samples = []
+    for k in range(2):
+        s = S.make_train_sample([10 + rank * 100 + k * TRAIN_BATCH + b for b in range(TRAIN_BATCH)], 1, view_seed=rank * 10 + k)
+        samples.append({key: torch.from_numpy(v).to(dev) for key, v in s.items()})
+    if impl == "ours":
+        from spsg_b200.train_step import ViewGuidedTrainStep
+        step = ViewGuidedTrainStep(net, loss_util, TRAIN_BATCH, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, cw,
+                                   max_num_locs_per_sample=MAX_LOCS, device=dev)
     else:
-        peak, which = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    alg_bytes = 116 * ctx["nv"] + 84 * ctx["rays"]
-    us = f_ms / max(f_n, 1) * 1e3
-    achieved = alg_bytes / (us * 1e-6) / 1e9 if us > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed ncu --set full captures
-    # (profiles/r01_c2_ncu_full_summary.md, r01_c3_ncu_full_summary.md); in C2 the 6.9 MB of images are still dirty
-    # in the 126 MB L2 when the kernel ends, so only the reads show up
-    traffic = {1: 2.52e6, 40: 397.4e6}.get(ctx["rays"] // (ctx["S"].WIDTH * ctx["S"].HEIGHT))
-    return {"bound": "hbm", "kernel": "raycast_forward_kernel", "achieved": round(achieved, 1), "peak": peak,
-            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": which,
-            "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": round(us, 2),
-            "backward_gather_us": round(g_ms / max(g_n, 1) * 1e3, 2),
-            "note": "not HBM-bound (traffic <= algorithmic bytes): instruction issue (C3) / dependent latency (C2), see DESIGN.md section 5 and profiles/README.md"}
+        from baseline.ref_train_step import RefTrainStep
+        step = RefTrainStep(net, TRAIN_BATCH, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, cw, native="reference",
+                            max_num_locs_per_sample=MAX_LOCS)
+
+    def one(i):
+        s = samples[i % 2]
+        # the reference's compute_targets clamps the target SDF in place (data_util.py:187-190): hand it a copy, like a
+        # dataloader's fresh batch
+        return step(dict(s, sdf=s["sdf"].clone()), optimizer=opt)
+
+    for i in range(warmup):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = one(i)
+    b.record()
+    torch.cuda.synchronize()
+    ms = reduce_max_ms(a.elapsed_time(b), dev, world)
+    return {"chunks_per_s": world * TRAIN_BATCH * steps / (ms * 1e-3), "unit": "chunks/s", "ms_per_step": ms / steps,
+            "steps": steps, "chunks_per_gpu_per_step": TRAIN_BATCH, "views_per_chunk": 1,
+            "generator_parameters": params, "num_locs_last_step": int(step.last.get("num_locs", -1)),
+            "last_loss": float(loss),
+            "step": ("spsg_b200.train_step.ViewGuidedTrainStep: reference Generator (baseline/_ref model.py, random init) "
+                     "fwd/bwd + its dense 3D losses + sparsify / normals / 3 raycasts / fused 2D losses of this package + Adam"
+                     if impl == "ours" else
+                     "baseline/ref_train_step.py: train.py:399-757 loop body on the reference's Generator, loss module, "
+                     "raycast_rgbd.py wrapper and CUDA extension + Adam"),
+            "collective": ("DistributedDataParallel, NCCL all-reduce of %.1f MB of gradients in one bucket, overlapped with "
+                           "backward" % (params * 4 / 1e6)) if world > 1 else "none (1 rank)"}
 
 
-def cpu_baseline(B, F, seconds=12.0):
+def cpu_raycast_baseline(seconds=12.0):
     """Scalar C restatement of the raycast fwd+bwd (oracle/raycast_oracle.c), OpenMP over pixels, host cores."""
     from oracle import oracle as O
     from spsg_b200 import synthetic as S
@@ -347,81 +474,238 @@ def cpu_baseline(B, F, seconds=12.0):
             break
     rays = S.WIDTH * S.HEIGHT * steps
     return {"value": rays / dt, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": "%d fwd+bwd steps of config c2 (one chunk, one 320x256 view) in %.1f s; forward OpenMP over "
-                      "pixels on %d threads, backward scalar" % (steps, dt, threads)}
+            "sample": "%d fwd+bwd steps of one chunk x one 320x256 view (the c3 batch is 40 such images) in %.1f s; forward "
+                      "OpenMP over pixels on %d threads, backward scalar" % (steps, dt, threads)}
 
 
-def run_reference(args, dev, rank, world, B, F, num_sets):
-    """The unmodified reference CUDA extension (oracle/_ref) in its wrapper's call order; one view per call as the
-    reference renders one view per chunk (F views = F calls)."""
-    from oracle import losses_ref as R
-    from oracle import ref_driver
+def cpu_generator_baseline(max_seconds=25.0):
+    """BASELINE configs[0]: reference Generator forward + class-weighted 3D semantic cross-entropy on one synthetic
+    64x64x128 chunk, batch 1, PyTorch CPU, default intra-op threads (2D losses off)."""
+    from baseline import ref_loader
     from spsg_b200 import synthetic as S
-    host = make_host_sets(num_sets, B, F, rank)
-    rays = B * F * S.WIDTH * S.HEIGHT
-    cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
-    ref = ref_driver.RefRaycaster(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST,
-                                  S.RAY_INCREMENT, MAX_LOCS, 64, device=dev)
-    devsets = [{k: v.to(dev) for k, v in h.items()} for h in host]
-    g = torch.Generator(device=dev).manual_seed(5)
-    grads = [torch.randn(s, device=dev, generator=g) for s in
-             ((B, S.HEIGHT, S.WIDTH, 3), (B, S.HEIGHT, S.WIDTH), (B, S.HEIGHT, S.WIDTH, 3), (B, S.HEIGHT, S.WIDTH, 14))]
-    sel = [torch.arange(B, device=dev) * F + f for f in range(F)]
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref is not installed on this box"}
+    model_util = ref_loader.load_module("model")
+    torch.manual_seed(7)
+    sys.stdout, keep = open(os.devnull, "w"), sys.stdout
+    try:
+        model = model_util.Generator(nf_in_geo=1, nf_in_color=4, nf=20, pass_geo_feats=True, truncation=S.TRUNCATION,
+                                     max_data_size=S.DIMS_ZYX)
+    finally:
+        sys.stdout = keep
+    model.eval()
+    s = S.make_train_sample([3], 1)
+    inputs, mask = torch.from_numpy(s["input"]), torch.from_numpy(s["mask"])
+    label = torch.from_numpy(s["semantics"])[:, 0]
+    cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32)
+    times_f, times_l = [], []
+    t_all = time.perf_counter()
+    with torch.no_grad():
+        for it in range(4):
+            t0 = time.perf_counter()
+            _, out_sdf, _, out_sem = model(inputs.clone(), mask, pred_sdf=[True, True], pred_color=True, pred_semantic=True)
+            t1 = time.perf_counter()
+            # train.py:494-509, 736-741: logits and labels at the predicted voxels, labelled ones only
+            locs = torch.nonzero(torch.abs(out_sdf[:, 0]) < S.TRUNCATION)
+            logits = out_sem[locs[:, 0], :, locs[:, 1], locs[:, 2], locs[:, 3]]
+            tgt = label[locs[:, 0], locs[:, 1], locs[:, 2], locs[:, 3]]
+            keep_rows = tgt < 14
+            loss = torch.nn.functional.cross_entropy(logits[keep_rows], tgt[keep_rows], weight=cw) if keep_rows.any() \
+                else torch.zeros(())
+            t2 = time.perf_counter()
+            if it > 0 or time.perf_counter() - t_all > max_seconds:
+                times_f.append(t1 - t0)
+                times_l.append(t2 - t1)
+            if time.perf_counter() - t_all > max_seconds:
+                break
+    f, l = float(np.median(times_f)), float(np.median(times_l))
+    return {"value": 1.0 / (f + l), "unit": "chunks/s", "cores": torch.get_num_threads(), "kind": "reference",
+            "generator_forward_s": f, "semantic_3d_ce_s": l, "voxels_in_loss": int(keep_rows.sum()),
+            "last_loss": float(loss),
+            "sample": "configs[0]: reference model.Generator (nf 20, random init) forward + class-weighted 3D cross-entropy "
+                      "on one synthetic 64x64x128 chunk, batch 1, PyTorch CPU with %d intra-op threads, median of %d passes"
+                      % (torch.get_num_threads(), len(times_f))}
 
-    def step_resident(i):
-        d = devsets[i % num_sets]
-        for f in range(F):
-            ref.forward(d["locs"], d["sdf"], d["color"], d["normal"], d["semantic"], d["view"][sel[f]].contiguous(),
-                        d["intr"][sel[f]].contiguous())
-            ref.backward(*grads)
 
-    result = torch.zeros(1, pin_memory=True)
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------------------
 
-    def step_e2e(i):
-        h = host[i % num_sets]
-        d = {k: h[k].to(dev, non_blocking=True) for k in H2D_KEYS}
+class Reference:
+    """The unmodified reference: its Python wrapper (baseline/_ref) when installed -- else its native entry points in the
+    wrapper's call order (oracle/ref_driver.py) -- on its CUDA extension; one view per call, as it renders."""
+
+    def __init__(self, dev, rank, B, F, num_sets):
+        from baseline import ref_loader
+        from oracle import losses_ref as R
+        from oracle import ref_driver
+        from spsg_b200 import synthetic as S
+        self.S, self.R, self.dev, self.B, self.F, self.num_sets = S, R, dev, B, F, num_sets
+        self.host = make_host_sets(num_sets, B, F, rank)
+        self.rays = B * F * S.WIDTH * S.HEIGHT
+        self.cw = torch.tensor(S.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
+        self.through_wrapper = ref_loader.available()
+        if self.through_wrapper:
+            wrapper = ref_loader.load_wrapper("reference")
+            self.ref = wrapper.RaycastRGBD(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST,
+                                           S.RAY_INCREMENT, max_num_locs_per_sample=MAX_LOCS)
+        else:
+            self.ref = ref_driver.RefRaycaster(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX,
+                                               S.THRESH_SAMPLE_DIST, S.RAY_INCREMENT, MAX_LOCS, 64, device=dev)
+        self.devsets = [self.split_views({k: v.to(dev) for k, v in h.items()}) for h in self.host]
+        g = torch.Generator(device=dev).manual_seed(5)
+        self.grads = [torch.randn(s, device=dev, generator=g) for s in
+                      ((B, S.HEIGHT, S.WIDTH, 3), (B, S.HEIGHT, S.WIDTH), (B, S.HEIGHT, S.WIDTH, 3), (B, S.HEIGHT, S.WIDTH, 14))]
+        self.nv = int(np.mean([d["locs"].shape[0] for d in self.devsets]))
+
+    def split_views(self, d):
+        """Per-view camera and target tensors (image i = chunk i // F, view i % F), made once per input set: the reference
+        takes one view per chunk and call."""
+        B, F = self.B, self.F
+        sel = [torch.arange(B, device=d["view"].device) * F + f for f in range(F)]
+        for k in ("view", "intr", "t_depth", "t_color", "t_label"):
+            d[k + "_v"] = [d[k][s].contiguous() for s in sel]
+        return d
+
+    def render(self, d, f, sdf, col, sem):
+        if self.through_wrapper:
+            return self.ref(d["locs"], sdf, col, d["normal"], sem, d["view_v"][f], d["intr_v"][f])
+        return self.ref.forward(d["locs"], sdf, col, d["normal"], sem, d["view_v"][f], d["intr_v"][f])
+
+    def step_resident(self, i):
+        """F x (forward + backward with upstream gradient images): the reference op boundary."""
+        d = self.devsets[i % self.num_sets]
+        for f in range(self.F):
+            if self.through_wrapper:
+                sdf, col, sem = (d[k].detach().requires_grad_(True) for k in ("sdf", "color", "semantic"))
+                out = self.render(d, f, sdf, col, sem)
+                torch.autograd.backward(out, self.grads)
+            else:
+                self.render(d, f, d["sdf"], d["color"], d["semantic"])
+                self.ref.backward(*self.grads)
+
+    def losses(self, d, f, out):
+        S, R = self.S, self.R
+        label = d["t_label_v"][f].unsqueeze(-1)
+        return R.depth_l1_loss(out[1], d["t_depth_v"][f].unsqueeze(1), S.VOXELSIZE) + \
+            R.compute_2dcolor_loss(out[0], d["t_color_v"][f], None) + R.semantic_2d_ce_loss(out[3], label, self.cw)
+
+    def step_fused_equivalent(self, d):
+        """F x (render + the literal depth / colour / 2D-semantic losses + backward to the voxels), train.py:626-643,744-757."""
         total = None
-        for f in range(F):
-            out = ref.forward(d["locs"], d["sdf"], d["color"], d["normal"], d["semantic"],
-                              d["view"][sel[f]].contiguous(), d["intr"][sel[f]].contiguous())
-            imgs = [o.detach().clone().requires_grad_(True) for o in out]
-            label = d["t_label"][sel[f]].unsqueeze(-1)
-            loss = R.depth_l1_loss(imgs[1], d["t_depth"][sel[f]].unsqueeze(1), S.VOXELSIZE) + \
-                R.compute_2dcolor_loss(imgs[0], d["t_color"][sel[f]], None) + \
-                R.semantic_2d_ce_loss(imgs[3], label, cw)
-            loss.backward()
-            ref.backward(imgs[0].grad, imgs[1].grad, torch.zeros_like(imgs[2]), imgs[3].grad)
+        for f in range(self.F):
+            sdf, col, sem = (d[k].detach().requires_grad_(True) for k in ("sdf", "color", "semantic"))
+            if self.through_wrapper:
+                out = self.render(d, f, sdf, col, sem)
+                loss = self.losses(d, f, out)
+                loss.backward()
+            else:
+                out = self.render(d, f, sdf, col, sem)
+                imgs = [o.detach().clone().requires_grad_(True) for o in out]
+                loss = self.losses(d, f, imgs)
+                loss.backward()
+                self.ref.backward(imgs[0].grad, imgs[1].grad, torch.zeros_like(imgs[2]), imgs[3].grad)
             total = loss.detach() if total is None else total + loss.detach()
-        result.copy_(total.reshape(1), non_blocking=True)
+        return total
 
-    def timed(fn, steps, warmup):
+    def e2e(self, world, steps, warmup):
+        """Same protocol as the product arm: one packed pinned buffer per set, copy stream, two device slots."""
+        dev, num_sets = self.dev, self.num_sets
+        result = torch.zeros((), pin_memory=True)
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        packed = [pack_host(h) for h in self.host]
+        cap = max(b.numel() for b, _ in packed)
+        slots = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def issue_copy(i):
+            slot, (buf, _) = i % 2, packed[i % num_sets]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                slots[slot][:buf.numel()].copy_(buf, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        def step(i, last):
+            slot = i % 2
+            if not last:
+                issue_copy(i + 1)
+            main.wait_event(copied[slot])
+            d = self.split_views(slot_views(slots[slot], packed[i % num_sets][1]))
+            total = self.step_fused_equivalent(d)
+            consumed[slot].record(main)
+            result.copy_(total.reshape(()), non_blocking=True)
+
+        def run(n):
+            for e in consumed:
+                e.record(main)
+            issue_copy(0)
+            for i in range(n):
+                step(i, i == n - 1)
+
+        return e2e_protocol(run, steps, warmup, dev, world)
+
+    def resident(self, world, steps, warmup):
         for i in range(max(3, warmup)):
-            fn(i)
+            self.step_resident(i)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(steps):
-            fn(i)
+            self.step_resident(i)
         b.record()
         torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return reduce_max_ms(a.elapsed_time(b), self.dev, world)
 
-    steps = max(1, min(args.steps, 60 if B * F == 1 else 10))
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole-room workload (BASELINE configs[4])
+# ---------------------------------------------------------------------------------------------------------------------
+
+def run_room(args, dev, rank, world, base):
+    from spsg_b200 import parallel as P
+    from spsg_b200 import room as R
+    dims = (128, 256, 320)
+    room = R.synthetic_room_sdf(dims, dev)
+    predict = R.synthetic_predictor(room)
+    kw = dict(views_per_chunk=5, chunks_per_launch=8, rank=rank, world=world)
+    windows = R.chunk_windows(dims)
+    mine = [windows[i] for i in P.shard_round_robin(len(windows), rank, world)]
+    predict.prepare_groups([mine[s:s + 8] for s in range(0, len(mine), 8)], (64, 64))
+    for _ in range(max(1, min(args.warmup, 3))):
+        out = R.render_room(predict, dims, dev, **kw)
     sampler = ClockSampler(dev.index)
     sampler.start()
-    ms = timed(step_resident, steps, args.warmup)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 20))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = R.render_room(predict, dims, dev, **kw)
+    b.record()
+    torch.cuda.synchronize()
     sampler.stop_flag = True
-    ms_e2e = float(np.median([timed(step_e2e, steps, min(args.warmup, 3)) for _ in range(E2E_REPEATS)]))
-    return dict(rays=rays, steps=steps, ms=ms, ms_e2e=ms_e2e, clocks=sampler.summary(),
-                h2d=bytes_of(host[0], H2D_KEYS), nv=int(np.mean([d["locs"].shape[0] for d in devsets])))
+    ms = reduce_max_ms(a.elapsed_time(b), dev, world)
+    rays = out["rays"]
+    if world > 1:
+        t = torch.tensor([float(rays)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        rays = float(t.item())
+    if rank == 0:
+        value = rays * reps / (ms * 1e-3)
+        print(json.dumps(dict(base, value=value, steps=reps, ms_per_step=ms / reps, clocks=sampler.summary(),
+                              e2e={"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 15 * 8,
+                                   "note": "a step is one whole room from the generator's dense heads (resident, as a generator "
+                                           "leaves them) to label maps + histogram read back; windows dealt round-robin to ranks"},
+                              gpu_launches=None, roofline=None)))
 
+
+# ---------------------------------------------------------------------------------------------------------------------
 
 def main():
     args = parse_args()
@@ -433,12 +717,29 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, F = (1, 1) if args.workload == "c2" else (8, 5)
     from spsg_b200 import synthetic as S
-    per_set_mb = 45.0 * B + 14.0 * B * F
-    num_sets = args.sets or max(2, int(np.ceil(190.0 / per_set_mb)))
-    config = {"workload": "%s: %d chunk(s) 64x64x128 x %d view(s) 320x256, depth+colour+normal+semantic, fwd+bwd"
-                          % (args.workload, B, F),
+    if args.workload == "c5":
+        config = {"workload": "c5: synthetic room 128x256x320 split into 64x64 windows (stride 32), 5 views 320x256 per window, "
+                              "sparsify + normals + raycast + label maps, windows sharded over ranks",
+                  "parallelism": "dp%d (windows round-robin)" % world,
+                  "l2": "one room's windows and images (> 1 GB) stream through between repeats"}
+        base = {"metric": "raycast rays/s (whole-room rendering)", "unit": "rays/s", "n_gpus": world, "warmup": args.warmup,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config}
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference's test_scene_as_chunks.py renders nothing "
+                                  "(SURVEY.md section 8 (iv)): there is no reference arm for c5"}))
+        else:
+            run_room(args, dev, rank, world, base)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    B, F = (1, 1) if args.workload == "c2" else (8, 5)
+    auto, per_set_mb = auto_sets(B, F)
+    num_sets = args.sets or auto
+    config = {"workload": "%s: %d chunk(s) 64x64x128 x %d view(s) 320x256, depth+colour+normal+semantic renderings, forward "
+                          "with fused depth/colour/2D-semantic losses + backward" % (args.workload, B, F),
               "chunks_per_step": B, "views_per_chunk": F, "rays_per_step": B * F * S.WIDTH * S.HEIGHT,
               "max_num_locs_per_sample": MAX_LOCS, "parallelism": "dp%d (independent chunk x view batches)" % world,
               "l2": "rotating %d distinct resident input sets (~%d MB > 126 MB L2) between timed steps"
@@ -450,21 +751,35 @@ def main():
     if args.impl == "reference":
         from oracle import ref_driver
         if ref_driver.available():
-            r = run_reference(args, dev, rank, world, B, F, num_sets)
-            value = world * r["rays"] * r["steps"] / (r["ms"] * 1e-3)
-            e2e = world * r["rays"] * r["steps"] / (r["ms_e2e"] * 1e-3)
-            line = dict(base, impl="reference", value=value, steps=r["steps"], ms_per_step=r["ms"] / r["steps"],
-                        clocks=r["clocks"], gpu_launches=0,
-                        e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4},
+            r = Reference(dev, rank, B, F, num_sets)
+            steps = max(1, min(args.steps, 60 if B * F == 1 else 12))  # bounded: the reference step is 10-25x longer
+            sampler = ClockSampler(dev.index)
+            sampler.start()
+            ms = r.resident(world, steps, args.warmup)
+            sampler.stop_flag = True
+            ms_e2e = r.e2e(world, steps, min(args.warmup, 3))
+            value = world * r.rays * steps / (ms * 1e-3)
+            e2e = world * r.rays * steps / (ms_e2e * 1e-3)
+            line = dict(base, impl="reference", value=value, steps=steps, ms_per_step=ms / steps,
+                        clocks=sampler.summary(), gpu_launches=0,
+                        e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(r.host[0], H2D_KEYS),
+                             "d2h_bytes_per_step": 4, "steps": steps, "ms_per_step": ms_e2e / steps,
+                             "api": "%s + literal depth/colour/semantic losses + backward, %d call(s) per step (one view "
+                                    "per chunk and call); inputs from one packed pinned buffer on a copy stream "
+                                    "(double-buffered), median of %d timed regions -- the product arm's protocol"
+                                    % ("reference RaycastRGBD wrapper (baseline/_ref)" if r.through_wrapper else
+                                       "reference native entry points (oracle/ref_driver.py)", F, E2E_REPEATS)},
                         cpu_baseline={"value": value, "unit": "rays/s", "cores": 1, "kind": "reference",
-                                      "sample": "reference CUDA extension (oracle/_ref, unmodified sources compiled "
-                                                "for sm_100) on the same B200: the reference has no CPU implementation "
-                                                "of this path; %d steps, max_num_locs_per_sample=%d as train.py:136"
-                                                % (r["steps"], MAX_LOCS)})
+                                      "sample": "reference CUDA extension (oracle/_ref, unmodified sources compiled for "
+                                                "sm_100) on the same B200: the reference has no CPU implementation of "
+                                                "this path; %d steps, max_num_locs_per_sample=%d as train.py:136"
+                                                % (steps, MAX_LOCS)})
+            if not args.no_train:
+                line["train"] = train_leg("reference", dev, rank, world, local, steps=4, warmup=2)
         else:
             if rank != 0:
                 return
-            c = cpu_baseline(B, F)
+            c = cpu_raycast_baseline()
             line = dict(base, impl="reference", value=c["value"], steps=1, ms_per_step=None, n_gpus=1,
                         clocks={"sm_mhz": None, "sm_max_mhz": None, "reasons": ["cpu run"]}, gpu_launches=0,
                         e2e={"value": c["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -475,27 +790,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    ctx = run_ours(args, dev, rank, B, F, num_sets)
+    o = Ours(dev, rank, B, F, num_sets)
     sampler = ClockSampler(dev.index)
     sampler.start()
-    ms = timed_graph(ctx, dev, world)
+    ms, steps, _ = measure_resident(o.step_fused, num_sets, dev, world, args.steps, args.warmup)
     sampler.stop_flag = True
-    steps = ctx["steps"]
-    value = world * ctx["rays"] * steps / (ms * 1e-3)
-    e2e_steps = max(10, min(steps, 100))
-    ms_e2e, last_loss = e2e_ours(ctx, dev, world, e2e_steps, min(args.warmup, 5))
-    e2e = world * ctx["rays"] * e2e_steps / (ms_e2e * 1e-3)
-    roof = roofline_ours(ctx, dev, min(steps, 50)) if rank == 0 else None
+    value = world * o.rays * steps / (ms * 1e-3)
+    e2e_steps = max(10, min(args.steps, 60))
+    ms_e2e, last_loss = o.e2e(world, e2e_steps, min(args.warmup, 5))
+    e2e = world * o.rays * e2e_steps / (ms_e2e * 1e-3)
+    roof = o.roofline(min(args.steps, 40), fused=True) if rank == 0 else None
+    extra = {}
+    if not args.no_secondary:
+        ms_u, steps_u, _ = measure_resident(o.step_unfused, num_sets, dev, world, args.steps, 3)
+        extra["unfused"] = {"value": world * o.rays * steps_u / (ms_u * 1e-3), "unit": "rays/s", "ms_per_step": ms_u / steps_u,
+                            "steps": steps_u, "note": "same workload at the reference op boundary: forward renders, backward "
+                                                      "takes four upstream gradient images (no fused losses)"}
+        if args.workload != "c2":
+            sets2, _ = auto_sets(1, 1)
+            o2 = Ours(dev, rank, 1, 1, sets2)
+            ms2, steps2, _ = measure_resident(o2.step_fused, sets2, dev, world, args.steps, 3)
+            extra["c2"] = {"workload": "c2: one chunk x one 320x256 view (BASELINE configs[1]), fused losses", "unit": "rays/s",
+                           "value": world * o2.rays * steps2 / (ms2 * 1e-3), "ms_per_step": ms2 / steps2, "steps": steps2}
+            del o2
+    # per step: fill, index, cell classes, forward, finalize_loss, gather
+    launches = 6
+    train = None
+    if not args.no_train:
+        del o.mods, o.devsets
+        torch.cuda.empty_cache()
+        train = train_leg("ours", dev, rank, world, local)
     if rank == 0:
         line = dict(base, value=value, steps=steps, ms_per_step=ms / steps, clocks=sampler.summary(),
-                    e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(ctx["host"][0], H2D_KEYS),
+                    e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(o.host[0], H2D_KEYS),
                          "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                          "api": "spsg_b200.losses.render_with_2d_losses (fused raycast + depth/colour/semantic losses) "
-                                "+ backward; every step's inputs copied from one packed pinned-host buffer on a copy stream (double-buffered); median of %d timed regions" % E2E_REPEATS,
+                                "+ backward; every step's inputs copied from one packed pinned-host buffer on a copy stream "
+                                "(double-buffered); median of %d timed regions" % E2E_REPEATS,
                          "last_loss": last_loss},
-                    gpu_launches=ctx["launches_per_step"] * steps, roofline=roof)
+                    gpu_launches=launches * steps, roofline=roof, **extra)
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(B, F)
+            line["cpu_baseline"] = dict(cpu_raycast_baseline(), generator_config1=cpu_generator_baseline())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

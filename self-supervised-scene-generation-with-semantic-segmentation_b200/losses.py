@@ -56,43 +56,84 @@ def _targets_struct(images, h, w, target_depth, target_color, weight_color, targ
     return t
 
 
+def _module_workspace(m):
+    ws = getattr(m, "workspace", None)
+    if ws is None:  # a raycaster-like object without one: give it one
+        ws = m.workspace = rc.ModuleWorkspace()
+    return ws
+
+
+def fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix, intrinsic_params, targets,
+                  clear_grads):
+    """``spsg_raycast_forward_loss`` on the buffers of raycaster ``m``: validates every tensor whose pointer crosses the
+    C ABI, renders, accumulates the 2D loss terms.  ``targets`` = (target_depth, target_color, weight_color, target_label,
+    class_weight, voxelsize, (w_depth, w_colour, w_semantic)).  Returns (params, targets struct, loss_out[8])."""
+    images = view_matrix.shape[0]
+    views = max(1, images // m.batch_size)
+    if images != views * m.batch_size or views > m.max_num_frames:
+        raise RuntimeError("view_matrix has %d images: expected batch_size (%d) x views <= max_num_frames (%d)"
+                           % (images, m.batch_size, m.max_num_frames))
+    n = rc.check_voxel_inputs(locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix, intrinsic_params,
+                              images)
+    if n * views > m.mapping3dto2d.shape[0]:
+        raise RuntimeError("too many voxels for raycast (%d x %d views > %d rows)" % (n, views, m.mapping3dto2d.shape[0]))
+    if clear_grads and (m.d_depth.shape[0] < n or m.d_color.shape[0] < n or m.d_normal.shape[0] < n or
+                        m.d_semantic.shape[0] < n):
+        raise RuntimeError("d_* buffers hold fewer than N = %d rows" % n)
+    dev = vals_sdf.device
+    if m.image_depth.device != dev:
+        raise RuntimeError("raycaster buffers live on %s, inputs on %s" % (m.image_depth.device, dev))
+    p = N.make_params(m.width, m.height, m.depth_min, m.depth_max, m.thresh_sample_dist, m.ray_increment,
+                      m.dims3d[2], m.dims3d[1], m.dims3d[0], m.batch_size, views, m.mapping3dto2d.shape[1], n, m.flags)
+    target_depth, target_color, weight_color, target_label, class_weight, voxelsize, weights = targets
+    tg = _targets_struct(images, m.height, m.width, target_depth, target_color, weight_color, target_label, class_weight,
+                         voxelsize, weights)
+    # terms, total and normalisers of THIS call (the backward reads the normalisers back)
+    loss_out = torch.empty(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+    gb = N.grad_buffers(m.d_color, m.d_depth, m.d_normal, m.d_semantic) if clear_grads else None
+    owner = _module_workspace(m)
+    with rc.device_guard(dev):
+        ws = owner.get(dev, N.workspace_bytes(p))
+        N.check(N.lib.spsg_raycast_forward_loss(
+            ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
+            N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
+            N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_normal), N.ptr(m.image_semantic),
+            N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(loss_out),
+            ctypes.byref(gb) if gb is not None else None, N.ptr(ws), ws.numel(), rc._stream(dev)))
+        owner.filled(p)
+    return p, tg, loss_out
+
+
+def fused_backward(m, p, tg, loss_out, grad_scale, grads_cleared):
+    """``spsg_raycast_backward_loss``: voxel gradients of ``grad_scale * total`` into rows [0, N) of ``m.d_*``."""
+    if grads_cleared:
+        p.flags |= N.SPSG_FLAG_GRADS_CLEARED
+    dev = m.image_depth.device
+    rc._check_input(grad_scale, "grad_scale")
+    rc._check_dtype(grad_scale, torch.float32, "grad_scale")
+    owner = _module_workspace(m)
+    with rc.device_guard(dev):
+        ws = owner.check(p, N.workspace_bytes(p))  # the work list of the forward that rendered m's images
+        N.check(N.lib.spsg_raycast_backward_loss(
+            ctypes.byref(p), N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_semantic),
+            ctypes.byref(tg), N.ptr(loss_out), N.ptr(grad_scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),
+            N.ptr(m.mapping3dto2d_num), N.ptr(m.d_color), N.ptr(m.d_depth), N.ptr(m.d_normal), N.ptr(m.d_semantic),
+            N.ptr(ws), ws.numel(), rc._stream(dev)))
+
+
 class FusedRaycastLossFunction(Function):
     @staticmethod
     def forward(ctx, raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix,
                 intrinsic_params, target_depth, target_color, weight_color, target_label, class_weight, voxelsize,
                 weights):
         m = raycaster
-        images = view_matrix.shape[0]
-        views = max(1, images // m.batch_size)
-        if images != views * m.batch_size or views > m.max_num_frames:
-            raise RuntimeError("view_matrix has %d images: expected batch_size (%d) x views <= max_num_frames (%d)"
-                               % (images, m.batch_size, m.max_num_frames))
         n = locs.shape[0]
-        if n * views > m.mapping3dto2d.shape[0]:
-            raise RuntimeError("too many voxels for raycast (%d x %d views > %d rows)" % (n, views, m.mapping3dto2d.shape[0]))
-        for t, name in ((locs, "locs"), (vals_sdf, "vals_sdf"), (vals_colors, "vals_colors"),
-                        (vals_normals, "vals_normals"), (vals_semantic, "vals_semantic"), (view_matrix, "view_matrix"),
-                        (intrinsic_params, "intrinsic_params")):
-            rc._check_input(t, name)
-        p = N.make_params(m.width, m.height, m.depth_min, m.depth_max, m.thresh_sample_dist, m.ray_increment,
-                          m.dims3d[2], m.dims3d[1], m.dims3d[0], m.batch_size, views, m.mapping3dto2d.shape[1], n,
-                          m.flags)
-        tg = _targets_struct(images, m.height, m.width, target_depth, target_color, weight_color, target_label,
-                             class_weight, voxelsize, weights)
-        dev = vals_sdf.device
-        # terms, total and normalisers of THIS call (the backward reads the normalisers back)
-        loss_out = torch.empty(N.SPSG_LOSS_OUT_FLOATS, device=dev)
+        images = view_matrix.shape[0]
         # a backward will follow: let the forward's fill pass clear the gradient rows it will write
         ctx.grads_cleared = any(ctx.needs_input_grad[2:6]) and n > 0
-        gb = N.grad_buffers(m.d_color, m.d_depth, m.d_normal, m.d_semantic) if ctx.grads_cleared else None
-        with rc.device_guard(dev):
-            ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
-            N.check(N.lib.spsg_raycast_forward_loss(
-                ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
-                N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
-                N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_normal), N.ptr(m.image_semantic),
-                N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(loss_out),
-                ctypes.byref(gb) if gb is not None else None, N.ptr(ws), ws.numel(), rc._stream(dev)))
+        p, tg, loss_out = fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix,
+                                        intrinsic_params, (target_depth, target_color, weight_color, target_label,
+                                                           class_weight, voxelsize, weights), ctx.grads_cleared)
         ctx.raycaster, ctx.params, ctx.targets, ctx.n, ctx.loss_out = m, p, tg, n, loss_out
         # keep the target tensors alive until backward (the struct only holds raw pointers)
         ctx.keep = (target_depth, target_color, weight_color, target_label, class_weight)
@@ -107,19 +148,32 @@ class FusedRaycastLossFunction(Function):
 
     @staticmethod
     def backward(ctx, grad_total, grad_terms, *unused):
-        m, p, tg, n = ctx.raycaster, ctx.params, ctx.targets, ctx.n
-        if ctx.grads_cleared:
-            p.flags |= N.SPSG_FLAG_GRADS_CLEARED
-        dev = m.image_depth.device
-        scale = grad_total.to(torch.float32).contiguous()
-        with rc.device_guard(dev):
-            ws = rc.workspace(dev, N.workspace_bytes(p), m.sparse_mapping)
-            N.check(N.lib.spsg_raycast_backward_loss(
-                ctypes.byref(p), N.ptr(m.image_color), N.ptr(m.image_depth), N.ptr(m.image_semantic),
-                ctypes.byref(tg), N.ptr(ctx.loss_out), N.ptr(scale), N.ptr(m.sparse_mapping), N.ptr(m.mapping3dto2d),
-                N.ptr(m.mapping3dto2d_num), N.ptr(m.d_color), N.ptr(m.d_depth), N.ptr(m.d_normal), N.ptr(m.d_semantic),
-                N.ptr(ws), ws.numel(), rc._stream(dev)))
+        m, n = ctx.raycaster, ctx.n
+        fused_backward(m, ctx.params, ctx.targets, ctx.loss_out, grad_total.to(torch.float32).contiguous(),
+                       ctx.grads_cleared)
         return (None, None, m.d_depth[:n], m.d_color[:n], m.d_normal[:n], m.d_semantic[:n]) + (None,) * 9
+
+
+def render_loss_and_voxel_grads(raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantics, view_matrix,
+                                intrinsic_params, images_depth=None, images_color=None, weight_color=None,
+                                target2d_label=None, weight_semantic_class=None, voxelsize=0.02, weight_depth_loss=1.0,
+                                weight_color_loss=1.0, weight_semantic_loss=1.0, grad_scale=None):
+    """The fused forward + backward pair without autograd, for callers that own the voxel tensors' gradients themselves
+    (and for CUDA-graph capture: nothing but the two native calls is enqueued).  Returns ``(loss_out, (d_sdf, d_color,
+    d_normal, d_semantic))``: ``loss_out[0:3]`` = depth / colour / semantic terms, ``loss_out[3]`` = weighted total; the
+    gradients of ``grad_scale * total`` (default 1) are views of rows [0, N) of the raycaster's ``d_*`` buffers."""
+    c = lambda t: None if t is None else t.contiguous()
+    m, n = raycaster, locs.shape[0]
+    p, tg, loss_out = fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantics, view_matrix,
+                                    intrinsic_params, (c(images_depth), c(images_color), c(weight_color), c(target2d_label),
+                                                       weight_semantic_class, voxelsize,
+                                                       (weight_depth_loss, weight_color_loss, weight_semantic_loss)), n > 0)
+    if grad_scale is None:
+        grad_scale = getattr(m, "_unit_scale", None)
+        if grad_scale is None or grad_scale.device != loss_out.device:
+            grad_scale = m._unit_scale = torch.ones((), device=loss_out.device)
+    fused_backward(m, p, tg, loss_out, grad_scale, n > 0)
+    return loss_out, (m.d_depth[:n], m.d_color[:n], m.d_normal[:n], m.d_semantic[:n])
 
 
 def render_with_2d_losses(raycaster, locs, vals_sdf, vals_colors, vals_normals, vals_semantics, view_matrix,

@@ -24,7 +24,7 @@ class RayCastRGBDFunction(Function):
     def forward(ctx, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, view_matrix_inv, intrinsic_params,
                 dims3d, width, height, depth_min, depth_max, thresh_sample_dist, ray_increment, image_color,
                 image_depth, image_normal, image_semantic, sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color,
-                d_depth, d_normal, d_semantic, views_per_chunk=1, flags=0):
+                d_depth, d_normal, d_semantic, views_per_chunk=1, flags=0, workspace_owner=None):
         if locs.shape[0] * views_per_chunk > mapping3dto2d.shape[0]:  # raycast_rgbd.py:16-21
             print('ERROR: locs size %s vs mapping3dto2d size %s' % (str(locs.shape), str(mapping3dto2d.shape)))
             keep = mapping3dto2d.shape[0] // views_per_chunk
@@ -43,7 +43,9 @@ class RayCastRGBDFunction(Function):
                                   vals_semantic, view_matrix_inv, image_color, image_depth, image_normal,
                                   image_semantic, mapping3dto2d, mapping3dto2d_num, intrinsic_params, opts,
                                   views_per_chunk=views_per_chunk, flags=flags, build_index=True,
-                                  clear_grads=(d_color, d_depth, d_normal, d_semantic) if ctx.grads_cleared else None)
+                                  clear_grads=(d_color, d_depth, d_normal, d_semantic) if ctx.grads_cleared else None,
+                                  workspace_owner=workspace_owner)
+        ctx.workspace_owner = workspace_owner
         ctx.dims = [sparse_mapping.shape[0], dims3d[2], dims3d[1], dims3d[0], num_locs]  # raycast_rgbd.py:30-31
         ctx.views_per_chunk = views_per_chunk
         ctx.save_for_backward(sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color, d_depth, d_normal,
@@ -60,7 +62,7 @@ class RayCastRGBDFunction(Function):
         raycast_rgbd_cuda.backward(
             grad_color.contiguous(), grad_depth.contiguous(), grad_normal.contiguous(), grad_semantic.contiguous(),
             sparse_mapping, mapping3dto2d, mapping3dto2d_num, ctx.dims, d_color, d_depth, d_normal, d_semantic,
-            views_per_chunk=ctx.views_per_chunk, grads_cleared=ctx.grads_cleared)
+            views_per_chunk=ctx.views_per_chunk, grads_cleared=ctx.grads_cleared, workspace_owner=ctx.workspace_owner)
         # raycast_rgbd.py:42-43: (locs, vals_sdf, vals_colors, vals_normals, vals_semantic, None...)
         return (None, d_depth[:n], d_color[:n], d_normal[:n], d_semantic[:n]) + \
                (None,) * (len(ctx.needs_input_grad) - 5)
@@ -98,6 +100,8 @@ class RaycastRGBD(nn.Module):
         self.d_depth = torch.zeros(batch_size * max_num_locs_per_sample, 1, device=device)
         self.d_semantic = torch.zeros(batch_size * max_num_locs_per_sample, 14, device=device)
         self.flags = 0
+        # scratch of the native calls (block maps, the backward's work list): owned by the module like the buffers above
+        self.workspace = raycast_rgbd_cuda.ModuleWorkspace()
 
     def get_max_num_locs_per_sample(self):
         return self.max_num_locs_per_sample
@@ -115,7 +119,7 @@ class RaycastRGBD(nn.Module):
                                          self.depth_max, self.thresh_sample_dist, self.ray_increment, self.image_color,
                                          self.image_depth, self.image_normal, self.image_semantic, self.sparse_mapping,
                                          self.mapping3dto2d, self.mapping3dto2d_num, self.d_color, self.d_depth,
-                                         self.d_normal, self.d_semantic, views, self.flags)
+                                         self.d_normal, self.d_semantic, views, self.flags, self.workspace)
 
 
 class RaycastOcc(nn.Module):

@@ -13,13 +13,21 @@ Same four entry points, positional tensors, in-place outputs and error behaviour
     raycast_occ(occ3d, occ2d, viewMatrixInv, intrinsicParams, opts)
 """
 import ctypes
-import weakref
+from collections import OrderedDict
 
 import torch
 
 from . import _native as N
 
-_workspaces = {}
+_MIN_TORCH = (2, 1)
+if tuple(int(x) for x in torch.__version__.split("+")[0].split(".")[:2]) < _MIN_TORCH:
+    raise ImportError("spsg_b200 needs torch >= %d.%d (found %s)" % (_MIN_TORCH + (torch.__version__,)))
+
+# Workspaces of callers that hold no module (the reference's wrapper talks to this module with bare tensors): strong
+# references keyed by the raycaster's `sparse_mapping` buffer, least recently used first, each stamped with the forward
+# that filled it.  `RaycastRGBD` (raycast_rgbd.py) and the fused losses pass their own workspace explicitly instead.
+_MAX_CACHED_WORKSPACES = 32
+_workspaces = OrderedDict()
 
 
 def _check_input(t, name):
@@ -35,22 +43,78 @@ def _check_dtype(t, dtype, name):
         raise RuntimeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
 
 
-def workspace(device, nbytes, owner=None):
-    """Scratch tensor of one raycaster (keyed by its ``sparse_mapping`` buffer), grown on demand; the C ABI never
-    allocates.  The forward leaves the backward's work list in it, so -- like the reference's ``mapping3dto2d``
-    tables (raycast_rgbd.py:29-32) -- it belongs to the module whose buffers the call pair uses.  Entries die with
-    their owner's storage."""
+def check_voxel_inputs(locs, vals_sdf, vals_color, vals_normals, vals_semantic, view_matrix, intrinsic_params, images):
+    """What every raw-pointer entry point relies on: CUDA + contiguous, int64 `locs` rows of 4, float32 payloads with at
+    least N rows of 1 / 3 / 3 / 14, cameras for every image.  Raises RuntimeError like the reference's AT_ASSERTM."""
+    for t, name in ((locs, "locs"), (vals_sdf, "vals_sdf"), (vals_color, "vals_color"), (vals_normals, "vals_normals"),
+                    (vals_semantic, "vals_semantic"), (view_matrix, "viewMatrixInv"), (intrinsic_params, "intrinsicParams")):
+        _check_input(t, name)
+    _check_dtype(locs, torch.int64, "locs")
+    for t, name in ((vals_sdf, "vals_sdf"), (vals_color, "vals_color"), (vals_normals, "vals_normals"),
+                    (vals_semantic, "vals_semantic"), (view_matrix, "viewMatrixInv"), (intrinsic_params, "intrinsicParams")):
+        _check_dtype(t, torch.float32, name)
+    n = locs.shape[0]
+    if locs.numel() != 4 * n:
+        raise RuntimeError("locs must be (N, 4) rows of (z, y, x, chunk)")
+    if vals_sdf.numel() < n or vals_color.numel() < 3 * n or vals_normals.numel() < 3 * n or vals_semantic.numel() < 14 * n:
+        raise RuntimeError("voxel value tensors hold fewer than N = %d rows" % n)
+    if view_matrix.numel() < images * 16 or intrinsic_params.numel() < images * 4:
+        raise RuntimeError("viewMatrixInv / intrinsicParams hold fewer than %d images" % images)
+    devs = {t.device for t in (locs, vals_sdf, vals_color, vals_normals, vals_semantic, view_matrix, intrinsic_params)}
+    if len(devs) != 1:
+        raise RuntimeError("raycast inputs live on different devices: %s" % sorted(str(d) for d in devs))
+    return n
+
+
+def _stamp(p):
+    return (int(p.num_locs), int(p.views_per_chunk), int(p.num_chunks), int(p.width), int(p.height),
+            int(p.max_pixels_per_voxel))
+
+
+def workspace(device, nbytes, owner=None, stamp=None, expect=None):
+    """Scratch tensor for callers without a module, keyed by the raycaster's ``sparse_mapping`` buffer and grown on demand;
+    the C ABI never allocates.  The forward leaves the backward's work list in it and records ``stamp`` (what it was run
+    with); the backward passes ``expect`` and gets an error -- not garbage -- if no forward with those parameters filled
+    the workspace of this raycaster."""
     key = (device.type, device.index, None if owner is None else owner.data_ptr())
     entry = _workspaces.get(key)
-    if entry is not None and entry[1] is not None and entry[1]() is None and owner is not None:
-        entry = None  # the buffer that owned this address is gone; the address now belongs to a new raycaster
-    if entry is None or entry[0].numel() < nbytes:
-        for k in [k for k, e in _workspaces.items() if e[1] is not None and e[1]() is None]:
-            del _workspaces[k]
-        ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-        entry = (ws, None if owner is None else weakref.ref(owner.untyped_storage()))
+    if expect is not None:
+        if entry is None or entry["stamp"] != expect or entry["ws"].numel() < nbytes:
+            raise RuntimeError("raycast backward without a matching forward on these buffers (forward ran with %s, backward "
+                               "asks for %s)" % (None if entry is None else entry["stamp"], expect))
+        _workspaces.move_to_end(key)
+        return entry["ws"]
+    if entry is None or entry["ws"].numel() < nbytes:
+        entry = {"ws": torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device), "stamp": None}
         _workspaces[key] = entry
-    return entry[0]
+        while len(_workspaces) > _MAX_CACHED_WORKSPACES:
+            _workspaces.popitem(last=False)
+    _workspaces.move_to_end(key)
+    if stamp is not None:
+        entry["stamp"] = stamp
+    return entry["ws"]
+
+
+class ModuleWorkspace:
+    """The workspace of one raycaster module: an explicit buffer it owns, stamped by every forward."""
+
+    def __init__(self):
+        self.ws, self.stamp = None, None
+
+    def get(self, device, nbytes):
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
+            self.ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+            self.stamp = None
+        return self.ws
+
+    def filled(self, p):
+        self.stamp = _stamp(p)
+
+    def check(self, p, nbytes):
+        if self.ws is None or self.stamp != _stamp(p) or self.ws.numel() < nbytes:
+            raise RuntimeError("raycast backward without a matching forward on this module (forward ran with %s, backward "
+                               "asks for %s)" % (self.stamp, _stamp(p)))
+        return self.ws
 
 
 def _stream(device):
@@ -102,44 +166,38 @@ def _forward_params(sparse_mapping, locs, mapping3dto2d, opts, views_per_chunk=1
 
 def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_semantic, viewMatrixInv, imageColor,
             imageDepth, imageNormal, imageSemantic, mapping3dto2d, mapping3dto2d_num, intrinsicParams, opts,
-            views_per_chunk=1, flags=0, build_index=False, clear_grads=None):
+            views_per_chunk=1, flags=0, build_index=False, clear_grads=None, workspace_owner=None):
     """Reference signature (``raycast_color_forward``, raycast_rgbd_cuda.cpp:57-91) plus keyword extensions with
     reference-preserving defaults.  ``clear_grads`` = (d_color, d_depth, d_normals, d_semantic) lets the forward's fill
-    pass clear the rows the matching ``backward(..., grads_cleared=True)`` will write (needs ``build_index=True``)."""
-    for t, name in ((sparse_mapping, "sparse_mapping"), (locs, "locs"), (vals_sdf, "vals_sdf"),
-                    (vals_color, "vals_color"), (vals_normals, "vals_normals"), (vals_semantic, "vals_semantic"),
-                    (viewMatrixInv, "viewMatrixInv"), (imageColor, "imageColor"), (imageDepth, "imageDepth"),
+    pass clear the rows the matching ``backward(..., grads_cleared=True)`` will write (needs ``build_index=True``).
+    ``workspace_owner`` = the calling module's ``ModuleWorkspace`` (else the scratch is looked up by ``sparse_mapping``)."""
+    for t, name in ((sparse_mapping, "sparse_mapping"), (imageColor, "imageColor"), (imageDepth, "imageDepth"),
                     (imageNormal, "imageNormal"), (imageSemantic, "imageSemantic"), (mapping3dto2d, "mapping3dto2d"),
-                    (mapping3dto2d_num, "mapping3dto2d_num"), (intrinsicParams, "intrinsicParams")):
+                    (mapping3dto2d_num, "mapping3dto2d_num")):
         _check_input(t, name)
     _check_dtype(sparse_mapping, torch.int32, "sparse_mapping")
-    _check_dtype(locs, torch.int64, "locs")
     _check_dtype(mapping3dto2d, torch.int32, "mapping3dto2d")
     _check_dtype(mapping3dto2d_num, torch.int32, "mapping3dto2d_num")
-    for t, name in ((vals_sdf, "vals_sdf"), (vals_color, "vals_color"), (vals_normals, "vals_normals"),
-                    (vals_semantic, "vals_semantic"), (viewMatrixInv, "viewMatrixInv"),
-                    (intrinsicParams, "intrinsicParams"), (imageColor, "imageColor"), (imageDepth, "imageDepth"),
-                    (imageNormal, "imageNormal"), (imageSemantic, "imageSemantic")):
+    for t, name in ((imageColor, "imageColor"), (imageDepth, "imageDepth"), (imageNormal, "imageNormal"),
+                    (imageSemantic, "imageSemantic")):
         _check_dtype(t, torch.float32, name)
     p = _forward_params(sparse_mapping, locs, mapping3dto2d, opts, views_per_chunk, flags)
     images = p.num_chunks * p.views_per_chunk
-    n = p.num_locs
+    n = check_voxel_inputs(locs, vals_sdf, vals_color, vals_normals, vals_semantic, viewMatrixInv, intrinsicParams, images)
     if mapping3dto2d_num.numel() < p.views_per_chunk * n or mapping3dto2d.shape[0] < p.views_per_chunk * n:
         raise RuntimeError("mapping3dto2d has %d rows, needs views_per_chunk*N = %d" %
                            (mapping3dto2d.shape[0], p.views_per_chunk * n))
-    if viewMatrixInv.numel() < images * 16 or intrinsicParams.numel() < images * 4:
-        raise RuntimeError("viewMatrixInv / intrinsicParams hold fewer than %d images" % images)
     px = images * p.width * p.height
     if imageDepth.numel() < px or imageColor.numel() < 3 * px or imageNormal.numel() < 3 * px or \
             imageSemantic.numel() < 14 * px:
         raise RuntimeError("image buffers are smaller than %d x %d x %d" % (images, p.height, p.width))
-    if vals_sdf.numel() < n or vals_color.numel() < 3 * n or vals_normals.numel() < 3 * n or \
-            vals_semantic.numel() < 14 * n:
-        raise RuntimeError("voxel value tensors hold fewer than N = %d rows" % n)
     dev = vals_sdf.device
     with device_guard(dev):
         nbytes = N.workspace_bytes(p)
-        ws = workspace(dev, nbytes, sparse_mapping)
+        if workspace_owner is not None:
+            ws = workspace_owner.get(dev, nbytes)
+        else:
+            ws = workspace(dev, nbytes, sparse_mapping, stamp=_stamp(p))
         args = (ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
                 N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(viewMatrixInv), N.ptr(intrinsicParams),
                 N.ptr(imageColor), N.ptr(imageDepth), N.ptr(imageNormal), N.ptr(imageSemantic),
@@ -149,6 +207,7 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
             if clear_grads is not None:
                 for t, rows in zip(clear_grads, (3, 1, 3, 14)):
                     _check_input(t, "clear_grads")
+                    _check_dtype(t, torch.float32, "clear_grads")
                     if t.numel() < n * rows:
                         raise RuntimeError("d_* buffers hold fewer than N = %d rows" % n)
                 gb = ctypes.byref(N.grad_buffers(*clear_grads))
@@ -157,11 +216,13 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
             if clear_grads is not None:
                 raise RuntimeError("clear_grads needs build_index=True")
             N.check(N.lib.spsg_raycast_forward(*args, N.ptr(ws), ws.numel(), _stream(dev)))
+        if workspace_owner is not None:
+            workspace_owner.filled(p)
     return ws
 
 
 def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping, mapping3dto2d, mapping3dto2d_num,
-             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1, grads_cleared=False):
+             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1, grads_cleared=False, workspace_owner=None):
     """Reference signature (``raycast_color_backward``, raycast_rgbd_cuda.cpp:102-140).
     ``dims`` = int32 CPU tensor (or sequence) [batch, Dx, Dy, Dz, N] (raycast_rgbd.py:30-31)."""
     for t, name in ((grad_color, "grad_color"), (grad_depth, "grad_depth"), (grad_normal, "grad_normal"),
@@ -169,6 +230,10 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                     (mapping3dto2d, "mapping3dto2d"), (mapping3dto2d_num, "mapping3dto2d_num"),
                     (d_color, "d_color"), (d_depth, "d_depth"), (d_normals, "d_normals"), (d_semantic, "d_semantic")):
         _check_input(t, name)
+    for t, name in ((grad_color, "grad_color"), (grad_depth, "grad_depth"), (grad_normal, "grad_normal"),
+                    (grad_semantic, "grad_semantic"), (d_color, "d_color"), (d_depth, "d_depth"), (d_normals, "d_normals"),
+                    (d_semantic, "d_semantic")):
+        _check_dtype(t, torch.float32, name)
     d = dims.tolist() if isinstance(dims, torch.Tensor) else list(dims)
     n = int(d[4])
     if d_color.shape[0] < n or d_depth.shape[0] < n or d_normals.shape[0] < n or d_semantic.shape[0] < n:
@@ -179,8 +244,14 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                       max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n,
                       flags=N.SPSG_FLAG_GRADS_CLEARED if grads_cleared else 0)
     dev = grad_color.device
+    px = sparse_mapping.shape[0] * views_per_chunk * p.width * p.height
+    if grad_depth.numel() < px or grad_color.numel() < 3 * px or grad_normal.numel() < 3 * px or grad_semantic.numel() < 14 * px:
+        raise RuntimeError("gradient images are smaller than %d x %d x %d" % (px // (p.width * p.height), p.height, p.width))
     with device_guard(dev):
-        ws = workspace(dev, N.workspace_bytes(p), sparse_mapping)
+        nbytes = N.workspace_bytes(p)
+        # the work list of the forward that rendered these images: refuse to run on anything else
+        ws = workspace_owner.check(p, nbytes) if workspace_owner is not None else \
+            workspace(dev, nbytes, sparse_mapping, expect=_stamp(p))
         N.check(N.lib.spsg_raycast_backward(ctypes.byref(p), N.ptr(grad_color), N.ptr(grad_depth), N.ptr(grad_normal),
                                             N.ptr(grad_semantic), N.ptr(sparse_mapping), N.ptr(mapping3dto2d),
                                             N.ptr(mapping3dto2d_num), N.ptr(d_color), N.ptr(d_depth),
