@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) backward_zero_kernel(const BackwardArgs a
 }
 
 // Upstream gradient of one pixel, all 21 channels (g[0..13] semantic, [14..16] colour, [17] depth->sdf, [18..20] normal).
-// Plain variant: read from the four gradient images.  Fused variant: recomputed from the rendering and the targets
-// of the 2D losses.
+// Plain variant: read from the four gradient images.  Fused variant (pixel_grads_fused): recomputed from the rendering and
+// the targets of the 2D losses.
 // per-term factors of the fused variant: weight * upstream scale / normaliser (loss_out[4..6]), hoisted out of the pixels
 struct FusedCoef { float sem, col, dep; };
 
@@ -67,9 +67,8 @@ __device__ __forceinline__ FusedCoef fused_coef(const BackwardArgs &a) {
     return c;
 }
 
-template <bool kFused>
-__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCoef &fc, unsigned gpix, float (&g)[21]) {
-    if (!kFused) {
+__device__ __forceinline__ void pixel_grads(const BackwardArgs &a, unsigned gpix, float (&g)[21]) {
+    {
         const float2 *s2 = reinterpret_cast<const float2 *>(a.grad_semantic + (size_t)gpix * 14);
 #pragma unroll
         for (int k = 0; k < 7; k++) {
@@ -80,54 +79,69 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCo
         g[14] = __ldg(c); g[15] = __ldg(c + 1); g[16] = __ldg(c + 2);
         g[17] = __ldg(a.grad_depth + gpix);
         g[18] = __ldg(n); g[19] = __ldg(n + 1); g[20] = __ldg(n + 2);
-    } else {
-        const LossArgs &L = a.loss;
+    }
+}
+
+// Fused variant: the pixel's 21 upstream gradients recomputed from the rendering and the 2D losses' targets, written
+// straight into the shared-memory row `t` term by term (no 21-register staging: the kernel stays at full occupancy).
+__device__ __forceinline__ void pixel_grads_fused(const BackwardArgs &a, const FusedCoef &fc, unsigned gpix, float *__restrict__ t) {
+    const LossArgs &L = a.loss;
+    // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
+    const int y = L.target_label ? (int)L.target_label[gpix] : 14;
+    bool sem_done = false;
+    if (y < 14) {
+        float l[14];
+        const float2 *s2 = reinterpret_cast<const float2 *>(a.image_semantic + (size_t)gpix * 14);
 #pragma unroll
-        for (int k = 0; k < 21; k++) g[k] = 0.0f;
-        // semantic: w[y] * (softmax - onehot) / sum_w   (d/dlogits of F.cross_entropy(..., weight), train.py:745)
-        const int y = L.target_label ? (int)L.target_label[gpix] : 14;
-        if (y < 14) {
-            float l[14];
-            const float2 *s2 = reinterpret_cast<const float2 *>(a.image_semantic + (size_t)gpix * 14);
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                const float2 t = __ldg(s2 + k);
-                l[2 * k] = t.x; l[2 * k + 1] = t.y;
-            }
-            if (l[0] != -CUDART_INF_F) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
-                float m = l[0];
-#pragma unroll
-                for (int k = 1; k < 14; k++) m = fmaxf(m, l[k]);
-                float sum = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 14; k++) {
-                    l[k] = expf(l[k] - m);
-                    sum += l[k];
-                }
-                const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
-                const float f = fc.sem * w, inv_sum = 1.0f / sum;
-#pragma unroll
-                for (int k = 0; k < 14; k++) g[k] = f * (l[k] * inv_sum - (k == y ? 1.0f : 0.0f));
-            }
+        for (int k = 0; k < 7; k++) {
+            const float2 v = __ldg(s2 + k);
+            l[2 * k] = v.x; l[2 * k + 1] = v.y;
         }
-        if (L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
-            const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+        if (l[0] != -CUDART_INF_F) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+            float m = l[0];
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float c = __ldg(a.image_color + (size_t)gpix * 3 + k);
-                const float d = __fadd_rn(__fmul_rn(c, w), -__fmul_rn(__ldg(L.target_color + (size_t)gpix * 3 + k), w));
-                if (c != -CUDART_INF_F) g[14 + k] = fc.col * w * (float)((d > 0.0f) - (d < 0.0f));  // valid = != -inf
+            for (int k = 1; k < 14; k++) m = fmaxf(m, l[k]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 14; k++) {
+                l[k] = __expf(l[k] - m);  // arguments <= 0; 2^-21 relative error, far inside the gradients' 1e-3 bar
+                sum += l[k];
             }
-        }
-        if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
-            const float t = __ldg(L.target_depth + gpix);
-            const float r = __ldg(a.image_depth + gpix);
-            if (t != 0.0f && r != -CUDART_INF_F) {
-                const float d = __fmul_rn(r, L.voxelsize) - t;
-                g[17] = fc.dep * (float)((d > 0.0f) - (d < 0.0f));
-            }
+            const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
+            const float f = fc.sem * w, fs = f * __frcp_rn(sum);
+#pragma unroll
+            for (int k = 0; k < 14; k++) t[k] = l[k] * fs - (k == y ? f : 0.0f);
+            sem_done = true;
         }
     }
+    if (!sem_done) {
+#pragma unroll
+        for (int k = 0; k < 14; k++) t[k] = 0.0f;
+    }
+    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+    if (L.target_color) {  // d/dc mean|c*w - t*w|  (loss.py:246-257)
+        const float w = L.weight_color ? __ldg(L.weight_color + gpix) : 1.0f;
+        const float *c = a.image_color + (size_t)gpix * 3, *tc = L.target_color + (size_t)gpix * 3;
+        const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+        const float d0 = __fadd_rn(__fmul_rn(c0, w), -__fmul_rn(__ldg(tc), w));
+        const float d1 = __fadd_rn(__fmul_rn(c1, w), -__fmul_rn(__ldg(tc + 1), w));
+        const float d2 = __fadd_rn(__fmul_rn(c2, w), -__fmul_rn(__ldg(tc + 2), w));
+        const float f = fc.col * w;
+        if (c0 != -CUDART_INF_F) g0 = f * (float)((d0 > 0.0f) - (d0 < 0.0f));  // valid = != -inf
+        if (c1 != -CUDART_INF_F) g1 = f * (float)((d1 > 0.0f) - (d1 < 0.0f));
+        if (c2 != -CUDART_INF_F) g2 = f * (float)((d2 > 0.0f) - (d2 < 0.0f));
+    }
+    t[14] = g0; t[15] = g1; t[16] = g2;
+    float gd = 0.0f;
+    if (L.target_depth) {  // d/ddepth mean|depth*voxelsize - t|  (train.py:635-638)
+        const float td = __ldg(L.target_depth + gpix);
+        const float r = __ldg(a.image_depth + gpix);
+        if (td != 0.0f && r != -CUDART_INF_F) {
+            const float d = __fmul_rn(r, L.voxelsize) - td;
+            gd = fc.dep * (float)((d > 0.0f) - (d < 0.0f));
+        }
+    }
+    t[17] = gd; t[18] = 0.0f; t[19] = 0.0f; t[20] = 0.0f;
 }
 
 // The gather (kernel.cu:391-419 turned inside out).  Work items are the (voxel, view) pairs the forward listed; one
@@ -140,7 +154,10 @@ __device__ __forceinline__ void pixel_grads(const BackwardArgs &a, const FusedCo
 constexpr int kGatherWarps = 8;
 
 template <bool kFused, bool kAtomic>
-__global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(const BackwardArgs a) {
+#ifndef SPSG_GATHER_MIN_BLOCKS
+#define SPSG_GATHER_MIN_BLOCKS 8  // 32 registers: full occupancy hides the dependent gathers (the fused variant spills ~150 B and is still faster)
+#endif
+__global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) backward_gather_kernel(const BackwardArgs a) {
     if ((int)blockIdx.x < a.zero_blocks) {
         zero_rows<true>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)a.zero_blocks * blockDim.x) >> 5);
         return;
@@ -158,6 +175,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
     int2 e = item < count ? a.list[item] : make_int2(0, 0);
     FusedCoef fc = {0.0f, 0.0f, 0.0f};
     if (kFused) fc = fused_coef(a);
+    // (Tried: a two-deep software pipeline that also fetches the next item's pixel count and first pixel ids ahead of time.
+    // Slower -- fused 161 -> 223 us, plain 105 -> 112 us on C3: it doubles the registers and halves the occupancy that
+    // hides these dependent loads in the first place.)
     while (item < count) {
         const int idx = e.x, img = e.y;
         const int next_item = item + groups_total;
@@ -171,10 +191,15 @@ __global__ void __launch_bounds__(kGatherWarps * 32) backward_gather_kernel(cons
         for (int k0 = 0; k0 < cnt; k0 += 16) {
             const int m = min(16, cnt - k0);
             if (hl < m) {
-                float g[21];
-                pixel_grads<kFused>(a, fc, pixbase + (unsigned)__ldg(prow + k0 + hl), g);
+                const unsigned gpix = pixbase + (unsigned)__ldg(prow + k0 + hl);
+                if (kFused) {
+                    pixel_grads_fused(a, fc, gpix, tile + hl * 21);
+                } else {
+                    float g[21];
+                    pixel_grads(a, gpix, g);
 #pragma unroll
-                for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
+                    for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
+                }
             }
             __syncwarp(hmask);
             for (int r = 0; r < m; r++) {

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) losses2d_backward_kernel(const BackwardAr
     const FusedCoef fc = fused_coef(a);
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < num_pixels; p += (long long)gridDim.x * blockDim.x) {
         float g[21];
-        pixel_grads<true>(a, fc, (unsigned)p, g);
+        pixel_grads_fused(a, fc, (unsigned)p, g);
         if (d_semantic) {
 #pragma unroll
             for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(d_semantic + p * 14)[k] = make_float2(g[2 * k], g[2 * k + 1]);
