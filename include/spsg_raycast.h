@@ -146,7 +146,10 @@ SPSG_API int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t 
  *    535-586): d_x[v] = sum over views of mean over the first min(num, max_pixels) pixels registered to
  *    voxel v of grad_x[pixel].  Rows [0, N) of every d_* are fully written (zeros where nothing hit);
  *    rows >= N are left untouched (the reference zero-fills the whole buffer, Python only ever
- *    returns [:N], raycast_rgbd.py:42).  Deterministic: no float atomics. */
+ *    returns [:N], raycast_rgbd.py:42).  With one view per chunk (the reference's case) the result is written with plain
+ *    stores from per-voxel sums accumulated in double precision: no float atomics, bit-identical from run to run.  With
+ *    several views per chunk the per-view means of a voxel are added with float atomics (one per view and channel), so the
+ *    last bit can vary with their order, like the reference's own atomics (tolerance 1e-3, BASELINE.json). */
 SPSG_API int spsg_raycast_backward(const spsg_raycast_params *p, const float *grad_color, const float *grad_depth,
                                    const float *grad_normal, const float *grad_semantic,
                                    const int32_t *sparse_mapping, const int32_t *mapping3dto2d,

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 const float kz = r.dz != 0.0f ? ((r.dz > 0.0f ? -kBoxEps : kBoxEps) - r.camz) * invz : kInf;
                 const int sxm = r.dx > 0.0f ? -1 : 0, sym = r.dy > 0.0f ? -1 : 0, szm = r.dz > 0.0f ? -1 : 0;
                 float ray = r.t0, t_end = active ? r.t1 : -kInf;
-                // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (Stepper): cap j so that
+                // A closed-form jump of j steps lands within j * ulp(ray) / 2 of ray + j * inc (step_advance): cap j so that
                 // this drift stays below kBoxEps / 4, far inside the kBoxEps the skip regions are shrunk by.
                 int jump_cap = 1 << 22;
                 {

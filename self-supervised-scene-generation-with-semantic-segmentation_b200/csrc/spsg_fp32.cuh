@@ -60,56 +60,7 @@ __device__ __forceinline__ Ray setup_ray(const float *__restrict__ M, const floa
 // fl(s + inc) = s + d with d = inc rounded to the u grid -- a constant as long as inc is not an exact tie
 // between two grid points -- and s + j*d is representable, so one fma reproduces j sequential adds as long
 // as every partial sum stays below 2^(e+1) - inc.  Anything irregular falls back to real adds.
-struct Stepper {
-    float inc, inv_inc;
-    float lo, hi, lim, d, inv_d;  // current binade [lo, hi = 2lo); closed form usable while ray < lim
-    bool regular;
-
-    __device__ __forceinline__ void init(float inc_) {
-        inc = inc_;
-        inv_inc = rcp_approx(inc_);
-        lo = 0.0f; hi = 0.0f; lim = 0.0f; d = inc_; inv_d = inv_inc; regular = false;
-    }
-    __device__ __forceinline__ void rebin(float ray) {
-        lo = __uint_as_float(__float_as_uint(ray) & 0x7f800000u);      // 2^e <= ray
-        hi = __fmul_rn(lo, 2.0f);
-        const float u = __fmul_rn(lo, 1.1920928955078125e-07f);         // 2^(e-23)
-        d = __fadd_rn(__fadd_rn(lo, inc), -lo);                         // inc on the u grid
-        const float rem = __fadd_rn(inc, -d);                           // exact remainder
-        regular = (lo >= 1.0f) && (lo <= 8388608.0f) && (inc > 0.0f) && (inc <= 0.25f * lo) && (d > 0.0f) &&
-                  (__fmul_rn(fabsf(rem), 2.0f) != u);
-        lim = __fadd_rn(hi, -__fmul_rn(inc, 2.0f));                    // partial sums must stay below 2lo - inc
-        inv_d = rcp_approx(d);
-    }
-    // exactly n >= 1 steps of `ray = ray + inc`
-    __device__ __forceinline__ float advance(float ray, int n) {
-        for (;;) {
-            if (n <= 2) {
-                ray = __fadd_rn(ray, inc);
-                if (n == 2) ray = __fadd_rn(ray, inc);
-                return ray;
-            }
-            if (!(ray >= lo && ray < hi)) rebin(ray);
-            int j = 0;
-            if (regular) {
-                // floor((lim - ray)/d) computed approximately; the slack inc + d in `lim` dwarfs the error
-                const float room = lim - ray;
-                j = (room > 0.0f) ? min(n, __float2int_rd(room * inv_d)) : 0;
-            }
-            if (j >= 1) {
-                ray = __fmaf_rn((float)j, d, ray);
-                n -= j;
-                if (n == 0) return ray;
-            } else {  // top of the binade (the add that crosses it rounds on the next grid), or an irregular binade
-                ray = __fadd_rn(ray, inc);
-                n -= 1;
-            }
-        }
-    }
-};
-
-// The same recurrence with the per-binade constants (they depend on inc only) tabulated once per CTA in shared
-// memory: entry e describes the binade [2^e, 2^(e+1)) as (d, 1/d, lim, top); lim = -inf marks a binade where the closed
+// The per-binade constants (they depend on inc only) are tabulated once per CTA in shared memory: entry e describes the binade [2^e, 2^(e+1)) as (d, 1/d, lim, top); lim = -inf marks a binade where the closed
 // form is not usable (entry 32 serves every ray parameter outside [1, 2^32); its "top" is 1).
 constexpr int kStepEntries = 33;
 

@@ -23,12 +23,14 @@ __global__ void __launch_bounds__(kTilePix) raycast_occ_kernel(const OccArgs a) 
     const unsigned ux = blockIdx.x * kTileW + (warp & 1) * 8 + (lane & 7);
     const unsigned uy = blockIdx.y * kTileH + (warp >> 1) * 4 + (lane >> 3);
     const int img = blockIdx.z;
+    __shared__ float4 s_steps[kStepEntries];
+    if (threadIdx.x < kStepEntries) step_table_fill(s_steps, threadIdx.x, a.inc);
+    __syncthreads();
     if (ux >= (unsigned)a.width || uy >= (unsigned)a.height) return;
     const Ray r = setup_ray(a.view_matrix + (size_t)img * 16, a.intrinsics + (size_t)img * 4, ux, uy, a.depth_min,
                             a.depth_max);
     const uint8_t *__restrict__ occ = a.occ3d + (size_t)img * a.dimz * a.dimy * a.dimx;
-    Stepper step;
-    step.init(a.inc);
+    const float inv_inc = rcp_approx(a.inc);
     float ray = r.t0, t_end = r.t1;
     if (!(a.flags & SPSG_FLAG_NO_CLIP)) {
         // nearest voxel is inside the grid only for p in (-0.5, dim-0.5)
@@ -54,8 +56,8 @@ __global__ void __launch_bounds__(kTilePix) raycast_occ_kernel(const OccArgs a) 
         } else {
             t_end = fminf(t_end, tout + margin);
             while (ray < tin - margin - a.inc && ray < t_end) {
-                const int want = max(1, min(__float2int_rd((tin - margin - ray) * step.inv_inc) - 1, 1 << 22));
-                ray = step.advance(ray, want);
+                const int want = max(1, min(__float2int_rd((tin - margin - ray) * inv_inc) - 1, 1 << 22));
+                ray = step_advance(s_steps, a.inc, ray, want);
             }
         }
     }

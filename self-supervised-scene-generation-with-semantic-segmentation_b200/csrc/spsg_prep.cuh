@@ -42,16 +42,21 @@ __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict_
                                                     int32_t *__restrict__ sparse_mapping,
                                                     const float *__restrict__ vals_sdf, float *__restrict__ dense,
                                                     int32_t *__restrict__ num, int views, int dimz, int dimy,
-                                                    int dimx) {
+                                                    int dimx, int num_chunks) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (num)
+        for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
     const longlong4 l = locs[i];  // (z, y, x, chunk)
     const long long z = l.x, y = l.y, x = l.z, b = l.w;
+    // A row outside the grid is skipped (the reference would write out of bounds, kernel.cu:355-359).  Duplicate rows are
+    // not supported: like the reference's scatter, the last writer wins, independently for the index and the brick.
+    if ((unsigned long long)z >= (unsigned long long)dimz || (unsigned long long)y >= (unsigned long long)dimy ||
+        (unsigned long long)x >= (unsigned long long)dimx || b < 0 || b >= num_chunks)
+        return;
     const long long cell = ((b * dimz + z) * dimy + y) * dimx + x;
     if (kWriteIndex) sparse_mapping[cell] = (int32_t)i;
     if (dense) dense[cell] = __ldg(vals_sdf + i);
-    if (num)
-        for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
 }
 
 // Block map.  bits of a region = OR over its cells of {1: positive cell, 2: negative cell, 4: mixed cell}.  A region

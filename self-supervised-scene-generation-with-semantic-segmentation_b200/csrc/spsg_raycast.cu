@@ -139,11 +139,11 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         if (build_index)
             index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
                                                        dense, mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
-                                                       p->dimx);
+                                                       p->dimx, p->num_chunks);
         else
             index_kernel<false><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
                                                         dense, mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
-                                                        p->dimx);
+                                                        p->dimx, p->num_chunks);
         CUDA_TRY(cudaGetLastError());
     }
     ForwardArgs a;
@@ -378,7 +378,7 @@ int spsg_build_index(const int64_t *locs, int64_t num_locs, int32_t *sparse_mapp
     CUDA_TRY(cudaMemsetAsync(sparse_mapping, 0xff, cells * sizeof(int32_t), st));
     if (num_locs > 0) {
         index_kernel<true><<<(unsigned)((num_locs + 255) / 256), 256, 0, st>>>(
-            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, nullptr, 0, dimz, dimy, dimx);
+            (const longlong4 *)locs, num_locs, sparse_mapping, nullptr, nullptr, nullptr, 0, dimz, dimy, dimx, num_chunks);
         CUDA_TRY(cudaGetLastError());
     }
     return SPSG_OK;

@@ -61,7 +61,16 @@ class Depth2Normals(torch.nn.Module):
             raise RuntimeError("depth must be a contiguous CUDA float32 tensor")
         if not intrinsic_params.is_cuda or not intrinsic_params.is_contiguous():
             raise RuntimeError("intrinsic_params must be a contiguous CUDA tensor")
+        if depth.dim() != 4 or depth.shape[1] != 1:
+            raise RuntimeError("depth must be (B,1,H,W)")
         b, _, h, w = depth.shape
+        # the native call writes filter_helper / camspace / normals rows for b x h x w pixels: they must fit the buffers
+        if b > self.normals.shape[0] or (h, w) != tuple(self.normals.shape[1:3]):
+            raise RuntimeError("depth is %dx%dx%d, this Depth2Normals was built for batches of up to %d frames of %dx%d"
+                               % (b, h, w, self.normals.shape[0], self.normals.shape[1], self.normals.shape[2]))
+        if intrinsic_params.dtype != torch.float32 or intrinsic_params.numel() < 4 * b or \
+                intrinsic_params.device != depth.device:
+            raise RuntimeError("intrinsic_params must be float32 (B,4) on the device of depth")
         dev = depth.device
         with torch.cuda.device(dev):
             N.check(N.lib.spsg_depth_to_normals(N.ptr(depth), N.ptr(intrinsic_params), N.ptr(self.filter_helper),
