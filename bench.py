@@ -49,6 +49,27 @@ MIN_REGION_S = 0.5     # the device-resident timed region lasts at least this lo
 TRAIN_BATCH = 8        # chunks per GPU and step of the train leg (BASELINE configs[2]/[3])
 
 
+def bind_to_gpu_numa_node(dev):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs NVML reports as local to its GPU -- what a
+    multi-GPU launcher does; on a two-socket 8-GPU box the host->device copies of the e2e leg otherwise cross the socket
+    interconnect.  Best effort: returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no NUMA-local CPUs reported"
+        os.sched_setaffinity(0, cpus)
+        return "bound to %d CPUs local to GPU %s" % (len(cpus), bus)
+    except Exception as e:  # NVML missing, container without the affinity syscall, ...
+        return "not bound (%s)" % type(e).__name__
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -715,6 +736,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: this implementation has no CPU path")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from spsg_b200 import synthetic as S
@@ -742,6 +764,7 @@ def main():
                           "with fused depth/colour/2D-semantic losses + backward" % (args.workload, B, F),
               "chunks_per_step": B, "views_per_chunk": F, "rays_per_step": B * F * S.WIDTH * S.HEIGHT,
               "max_num_locs_per_sample": MAX_LOCS, "parallelism": "dp%d (independent chunk x view batches)" % world,
+              "host_affinity": numa,
               "l2": "rotating %d distinct resident input sets (~%d MB > 126 MB L2) between timed steps"
                     % (num_sets, int(per_set_mb * num_sets))}
     base = {"metric": "raycast fwd+bwd rays/s", "unit": "rays/s", "n_gpus": world, "warmup": args.warmup,

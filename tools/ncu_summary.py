@@ -2,6 +2,7 @@
 """Condense an `ncu --set full` report into the per-kernel numbers DESIGN.md / bench.py quote.
 
 usage: tools/ncu_summary.py <report.ncu-rep> [out.md]
+       tools/ncu_summary.py --traffic <workload> <report.ncu-rep> <summary.md name> <kernel regex>   (updates profiles/ncu_traffic.json)
 One block per profiled launch: duration, issue/IPC, thread efficiency, occupancy, L1/L2 hit rates, DRAM bytes
 (= bench.py's roofline.traffic), top stall reasons.  Reads the report with `ncu -i ... --page raw --csv`."""
 import csv
@@ -43,7 +44,29 @@ WANT = [
 ]
 
 
+def traffic(workload, rep, summary, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch matching `kernel`, per launch, into
+    profiles/ncu_traffic.json (bench.py's roofline.traffic reads it)."""
+    import json, os, re
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    iN, iR, iW = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [(float(r[iR].replace(",", "")) * scale[units[iR]] + float(r[iW].replace(",", "")) * scale[units[iW]], r[iN])
+            for r in rows[2:] if re.search(kernel, r[iN])]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    data = json.load(open(path)) if os.path.isfile(path) else {}
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    data[workload] = {"dram_bytes_per_launch": sum(v for v, _ in vals) / len(vals), "launches_averaged": len(vals),
+                      "kernel": vals[0][1].replace("<unnamed>::", ""), "summary": summary, "captured_at_commit": commit}
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    print(path, data[workload])
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(*sys.argv[2:6])
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
