@@ -322,6 +322,72 @@ class Ours:
 
         return e2e_protocol(run, steps, warmup, dev, world), float(result)
 
+    def e2e_device_flow(self, world, steps, warmup):
+        """The training data flow: the voxel tensors never come from the host -- the generator leaves dense heads (SDF,
+        colour, 14 logits per cell) in HBM -- and only the step's frames (depth, colour, labels, cameras) do.  Per step:
+        host -> device copy of the frames (pinned, copy stream, two slots), then on the device the stream-compaction
+        sparsify of the heads (train.py:494-509; its one host read of N included), the sparse normals (loss.py:285-306),
+        the fused raycast + 2D losses, the backward down to dense head gradients, and the loss read back."""
+        from spsg_b200 import normals as NRM
+        from spsg_b200 import sparsify as SP
+        S, render, mods, host, cw, dev, B, F = self.S, self.render, self.mods, self.host, self.cw, self.dev, self.B, self.F
+        num_sets = len(host)
+        dz, dy, dx = S.DIMS_ZYX
+        heads = []
+        for h in host:  # dense heads of every input set, made once: they are the generator's (resident) output
+            locs = h["locs"].to(dev)
+            idx = (locs[:, 3], locs[:, 0], locs[:, 1], locs[:, 2])
+            sdf = torch.full((B, dz, dy, dx), 2.0 * S.TRUNCATION, device=dev)
+            sdf[idx] = h["sdf"].to(dev)[:, 0]
+            col = torch.zeros(B, dz, dy, dx, 3, device=dev)
+            col[idx] = h["color"].to(dev)
+            sem = torch.zeros(B, dz, dy, dx, 14, device=dev)
+            sem[idx] = h["semantic"].to(dev)
+            heads.append((sdf.unsqueeze(1).contiguous(), col.permute(0, 4, 1, 2, 3).contiguous(),
+                          sem.permute(0, 4, 1, 2, 3).contiguous()))
+        keys = ("view", "intr", "t_depth", "t_color", "t_label")
+        packed = [pack_host(h, keys) for h in host]
+        cap = max(b.numel() for b, _ in packed)
+        slots = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        result = torch.zeros((), pin_memory=True)
+
+        def issue_copy(i):
+            slot, (buf, _) = i % 2, packed[i % num_sets]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                slots[slot][:buf.numel()].copy_(buf, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        def step(i, last):
+            slot, k = i % 2, i % num_sets
+            if not last:
+                issue_copy(i + 1)
+            main.wait_event(copied[slot])
+            d = slot_views(slots[slot], packed[k][1])
+            sdf, col, sem = (t.detach().requires_grad_(True) for t in heads[k])
+            locs, v_sdf, v_col, v_sem = SP.sparsify_predictions(sdf, S.TRUNCATION, None, col, sem)
+            nrm = NRM.compute_normals_sparse(locs, v_sdf, S.DIMS_ZYX, transform=torch.inverse(d["view"][::F]), num_chunks=B)
+            total, _, _ = render(mods[k], locs, v_sdf, v_col, nrm, v_sem, d["view"], d["intr"], images_depth=d["t_depth"],
+                                 images_color=d["t_color"], target2d_label=d["t_label"], weight_semantic_class=cw,
+                                 voxelsize=S.VOXELSIZE)
+            total.backward()
+            consumed[slot].record(main)
+            result.copy_(total.detach(), non_blocking=True)
+
+        def run(n):
+            for e in consumed:
+                e.record(main)
+            issue_copy(0)
+            for i in range(n):
+                step(i, i == n - 1)
+
+        ms = e2e_protocol(run, steps, warmup, dev, world)
+        return ms, float(result), bytes_of(host[0], keys)
+
     def roofline(self, steps, fused):
         """Dominant kernel (raycast forward) alone: CUDA events around each launch on its stream, inputs rotated."""
         N = self.N
@@ -363,10 +429,10 @@ def ncu_traffic(workload):
         return None, "no committed ncu capture for this workload"
 
 
-def pack_host(h):
+def pack_host(h, keys=H2D_KEYS):
     """One pinned host buffer per input set (256-byte aligned fields, what a loader thread would hand over)."""
     off, fields = 0, {}
-    for k in H2D_KEYS:
+    for k in keys:
         nbytes = h[k].numel() * h[k].element_size()
         fields[k] = (off, nbytes, h[k].dtype, tuple(h[k].shape))
         off += (nbytes + 255) // 256 * 256
@@ -824,6 +890,15 @@ def main():
     e2e = world * o.rays * e2e_steps / (ms_e2e * 1e-3)
     roof = o.roofline(min(args.steps, 40), fused=True) if rank == 0 else None
     extra = {}
+    if not args.no_secondary:
+        ms_f, loss_f, h2d_f = o.e2e_device_flow(world, max(10, min(args.steps, 40)), 3)
+        n_f = max(10, min(args.steps, 40))
+        extra["e2e_train_flow"] = {
+            "value": world * o.rays * n_f / (ms_f * 1e-3), "unit": "rays/s", "ms_per_step": ms_f / n_f, "steps": n_f,
+            "h2d_bytes_per_step": h2d_f, "d2h_bytes_per_step": 4, "last_loss": loss_f,
+            "api": "dense generator heads resident in HBM -> spsg_b200.sparsify.sparsify_predictions -> normals."
+                   "compute_normals_sparse -> losses.render_with_2d_losses -> backward to dense head gradients; only the "
+                   "step's frames (depth, colour, labels, cameras) are copied from pinned host memory"}
     if not args.no_secondary:
         ms_u, steps_u, _ = measure_resident(o.step_unfused, num_sets, dev, world, args.steps, 3)
         extra["unfused"] = {"value": world * o.rays * steps_u / (ms_u * 1e-3), "unit": "rays/s", "ms_per_step": ms_u / steps_u,

@@ -6,12 +6,11 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 
-args = bench.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-B, F = (1, 1) if args.workload == "c2" else (8, 5)
-ctx = bench.run_ours(args, dev, 0, B, F, 2)
-S, render, mods, host, cw = ctx["S"], ctx["render"], ctx["mods"], ctx["host"], ctx["cw"]
+B, F = (8, 5) if "--c3" in sys.argv else (1, 1)
+o = bench.Ours(dev, 0, B, F, 2)
+S, render, mods, host, cw = o.S, o.render, o.mods, o.host, o.cw
 d = {k: host[0][k].to(dev) for k in bench.H2D_KEYS}
 m = mods[0]
 T = {}
