@@ -627,7 +627,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 const long long clk_e2 = clock64();
 #endif
 
+                // the staging buffer is reused: semantic first, then colour + normal + depth
+                const bool vec = a.vec_ok != 0;
+                const size_t tile_pix0 = ((size_t)img * a.height + wy0) * a.width + wx0;
+#pragma unroll
+                for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(stage + lane * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
+                __syncwarp();
+                store_warp_tile<14>(stage, a.image_semantic, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
                 if (kLoss) {
+                    // The three 2D loss terms of this pixel.  The logits are read back from the staging row (still intact: the
+                    // stores above only read it), one at a time, so the 14 payload registers are dead by now and the fused
+                    // variant needs no more registers than the plain one.
                     float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
                     if (hit >= 0) {
                         const LossArgs &L = a.loss;
@@ -645,25 +655,29 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                         }
                         if (L.target_label) {  // train.py:744-746
                             const int y = L.target_label[gpix];
-                            if (y < 14 && sem[0] != ninf) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
-                                float m = sem[0];
+                            const float *lg = stage + lane * 14;
+                            if (y < 14 && lg[0] != ninf) {  // valid = (label < 14) & (logit0 != -inf), train.py:744
+                                float m = lg[0];
 #pragma unroll
-                                for (int k = 1; k < 14; k++) m = fmaxf(m, sem[k]);
-                                float s = 0.0f, ly = 0.0f;
+                                for (int k = 1; k < 14; k++) m = fmaxf(m, lg[k]);
+                                float s = 0.0f;
 #pragma unroll
-                                for (int k = 0; k < 14; k++) {
-                                    s += expf(sem[k] - m);
-                                    if (k == y) ly = sem[k];
-                                }
+                                for (int k = 0; k < 14; k++) s += __expf(lg[k] - m);  // arguments <= 0, the largest term is exactly 1:
+                                // relative error of the sum <= 2^-21, of the loss far below the 1e-5 it is checked to
                                 const float w = L.class_weight ? __ldg(L.class_weight + y) : 1.0f;
-                                acc[4] = w * (logf(s) + m - ly);
+                                acc[4] = w * (__logf(s) + m - lg[y]);
                                 acc[5] = w;
                             }
                         }
                     }
+                    // the two pixel counts are ballots, the four sums shuffle trees
                     float mine = 0.0f;
+                    const int n_depth = __popc(__ballot_sync(kFull, acc[1] != 0.0f)), n_color = __popc(__ballot_sync(kFull, acc[3] != 0.0f));
+                    if (lane == 1) mine = (float)n_depth;
+                    if (lane == 3) mine = 3.0f * (float)n_color;
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
+                        if (k == 1 || k == 3) continue;
                         const float t = warp_sum(acc[k]);
                         if (lane == k) mine = t;
                     }
@@ -671,13 +685,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                     const unsigned slot = ((unsigned)tile * 7u + (unsigned)img * 11u) % kLossSlots;
                     if (lane < 6 && mine != 0.0f) atomicAdd(a.loss.accum + slot * 8 + lane, (double)mine);
                 }
-                // the staging buffer is reused: semantic first, then colour + normal + depth
-                const bool vec = a.vec_ok != 0;
-                const size_t tile_pix0 = ((size_t)img * a.height + wy0) * a.width + wx0;
-#pragma unroll
-                for (int k = 0; k < 7; k++) reinterpret_cast<float2 *>(stage + lane * 14)[k] = make_float2(sem[2 * k], sem[2 * k + 1]);
-                __syncwarp();
-                store_warp_tile<14>(stage, a.image_semantic, tile_pix0, wx0, wy0, a.width, a.height, vec, lane);
                 __syncwarp();
                 float *s_col = stage, *s_nrm = stage + 96, *s_dep = stage + 192;
                 s_col[lane * 3 + 0] = col0; s_col[lane * 3 + 1] = col1; s_col[lane * 3 + 2] = col2;
