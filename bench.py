@@ -769,7 +769,15 @@ def run_room(args, dev, rank, world, base):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    reps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    R.render_room(predict, dims, dev, **kw)
+    torch.cuda.synchronize()
+    one = max(time.perf_counter() - t0, 1e-4)
+    reps = max(3, min(args.steps, 20), int(math.ceil(MIN_REGION_S / one)))  # a timed region of at least MIN_REGION_S
+    if world > 1:  # the same count on every rank
+        t = torch.tensor([reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps = int(t.item())
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
