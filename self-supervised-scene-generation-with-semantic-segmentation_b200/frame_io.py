@@ -32,124 +32,123 @@ def _executor(workers):
 
 
 def read_frame_file(filename, randomize, max_num_frames):
-    """data_util.py:764-771: one frame id per line, -1 = unusable; optionally shuffled."""
-    with open(filename) as f:
-        frames = [int(line) for line in f.read().splitlines()]
+    """Frame ids of one chunk (data_util.py:764-771): one integer per line, -1 marks an unusable frame; with ``randomize``
+    the usable ids are shuffled (Python's ``random``, like the reference) before the first ``max_num_frames`` are taken."""
+    with open(filename) as fh:
+        ids = [int(tok) for tok in fh.read().split()]
     if randomize:
-        frames = np.array(frames)
-        frames = frames[frames != -1]
-        random.shuffle(frames)
-    return frames[:max_num_frames]
+        ids = np.array(ids)
+        ids = ids[ids != -1]
+        random.shuffle(ids)
+    return ids[:max_num_frames]
+
+
+def _matrix_rows(path):
+    with open(path) as fh:
+        return np.asarray([ln.split(" ")[:4] for ln in fh.read().splitlines()], dtype=np.float32)
 
 
 def read_camera_file(filename, intrinsic_filename=None):
-    """data_util.py:774-787: 4 rows of pose (camera -> world) followed by 4 rows of intrinsics."""
-    def rows(name):
-        with open(name) as f:
-            return np.asarray([line.split(" ")[:4] for line in f.read().splitlines()], dtype=np.float32)
-    lines = rows(filename)
-    pose = torch.from_numpy(lines[:4].copy())
-    intrinsic = torch.from_numpy(lines[4:].copy()) if intrinsic_filename is None else \
-        torch.from_numpy(rows(intrinsic_filename)[:4].copy())
-    return pose, intrinsic
+    """(pose, intrinsic) of one frame (data_util.py:774-787): the camera file holds the 4x4 camera -> world pose followed by
+    the 4x4 intrinsic matrix; a separate intrinsic file overrides the latter."""
+    rows = _matrix_rows(filename)
+    k_rows = rows[4:] if intrinsic_filename is None else _matrix_rows(intrinsic_filename)[:4]
+    return torch.from_numpy(rows[:4].copy()), torch.from_numpy(k_rows.copy())
+
+
+def _resized_width(src_wh, dst_wh):
+    # width after scaling the source to the target height (aspect ratio kept), data_util.py:794 / :806
+    return int(math.floor(dst_wh[1] * float(src_wh[0]) / float(src_wh[1])))
 
 
 def resize_crop_image(image, new_image_dims):
-    """data_util.py:790-800 for a decoded array (h, w[, c]); ``new_image_dims`` = [width, height].  Nearest-neighbour
-    resize to the new height, then a centre crop to the new width (torchvision's Resize / CenterCrop on PIL images)."""
-    image_dims = [image.shape[1], image.shape[0]]
-    if image_dims == list(new_image_dims):
+    """Nearest-neighbour resize of a decoded array (h, w[, c]) to the target height, then a centre crop to the target width
+    (data_util.py:790-800: torchvision's Resize / CenterCrop on PIL images); ``new_image_dims`` = [width, height]."""
+    tw, th = int(new_image_dims[0]), int(new_image_dims[1])
+    if [image.shape[1], image.shape[0]] == [tw, th]:
         return image
-    resize_width = int(math.floor(new_image_dims[1] * float(image_dims[0]) / float(image_dims[1])))
-    pil = Image.fromarray(image).resize((resize_width, new_image_dims[1]), Image.NEAREST)
-    if pil.size[0] == new_image_dims[1] and pil.size[1] == new_image_dims[0]:
-        return pil  # (the reference returns the PIL image in this corner case, data_util.py:796-797)
-    th, tw = new_image_dims[1], new_image_dims[0]
-    w, h = pil.size
-    if tw > w or th > h:  # torchvision's CenterCrop pads with zeros first
-        pad_l, pad_t = max((tw - w) // 2, 0), max((th - h) // 2, 0)
-        padded = Image.new(pil.mode, (max(w, tw), max(h, th)))
-        padded.paste(pil, (pad_l, pad_t))
-        pil, (w, h) = padded, padded.size
-    top, left = int(round((h - th) / 2.0)), int(round((w - tw) / 2.0))
-    return np.array(pil.crop((left, top, left + tw, top + th)))
+    scaled = Image.fromarray(image).resize((_resized_width((image.shape[1], image.shape[0]), (tw, th)), th), Image.NEAREST)
+    w, h = scaled.size
+    if (w, h) == (th, tw):
+        return scaled  # the reference returns the PIL image itself in this corner case (data_util.py:796-797)
+    if tw > w or th > h:  # CenterCrop pads a smaller image with zeros first
+        canvas = Image.new(scaled.mode, (max(w, tw), max(h, th)))
+        canvas.paste(scaled, (max((tw - w) // 2, 0), max((th - h) // 2, 0)))
+        scaled, (w, h) = canvas, canvas.size
+    x0, y0 = int(round((w - tw) / 2.0)), int(round((h - th) / 2.0))
+    return np.array(scaled.crop((x0, y0, x0 + tw, y0 + th)))
 
 
 def adjust_intrinsic(intrinsic, intrinsic_image_dim, image_dim):
-    """data_util.py:803-812 (modifies and returns ``intrinsic``)."""
-    if list(intrinsic_image_dim) == list(image_dim):
-        return intrinsic
-    resize_width = int(math.floor(image_dim[1] * float(intrinsic_image_dim[0]) / float(intrinsic_image_dim[1])))
-    intrinsic[0, 0] *= float(resize_width) / float(intrinsic_image_dim[0])
-    intrinsic[1, 1] *= float(image_dim[1]) / float(intrinsic_image_dim[1])
-    intrinsic[0, 2] *= float(image_dim[0] - 1) / float(intrinsic_image_dim[0] - 1)
-    intrinsic[1, 2] *= float(image_dim[1] - 1) / float(intrinsic_image_dim[1] - 1)
+    """Intrinsics of the resized + cropped frame (data_util.py:803-812); modifies and returns ``intrinsic``."""
+    src, dst = list(intrinsic_image_dim), list(image_dim)
+    if src != dst:
+        intrinsic[0, 0] *= float(_resized_width(src, dst)) / float(src[0])
+        intrinsic[1, 1] *= float(dst[1]) / float(src[1])
+        intrinsic[0, 2] *= float(dst[0] - 1) / float(src[0] - 1)  # (the crop is accounted for here)
+        intrinsic[1, 2] *= float(dst[1] - 1) / float(src[1] - 1)
     return intrinsic
 
 
 def load_frame(depth_file, color_file, camera_file, depth_image_dims, color_image_dims, normalize, load_depth, load_color,
                intrinsic_file=None):
-    """data_util.py:837-859."""
+    """One frame (data_util.py:837-859): depth in metres (16-bit millimetres / 1000), colour (3,H,W) in [0,1] (optionally
+    normalised), pose, intrinsic adjusted to the colour frame's size."""
     pose, intrinsic = read_camera_file(camera_file, intrinsic_file)
-    depth_image = color_image = orig_dims = None
+    depth_t = color_t = src_wh = None
     if load_depth:
-        depth = np.array(Image.open(depth_file))
-        orig_dims = [depth.shape[1], depth.shape[0]]
-        depth = np.asarray(resize_crop_image(depth, list(depth_image_dims)))
-        depth_image = torch.from_numpy(depth.astype(np.float32) / 1000.0)
+        raw = np.array(Image.open(depth_file))
+        src_wh = [raw.shape[1], raw.shape[0]]
+        mm = np.asarray(resize_crop_image(raw, list(depth_image_dims)))
+        depth_t = torch.from_numpy(mm.astype(np.float32) / 1000.0)
     if load_color:
-        color = np.array(Image.open(color_file))
-        orig_dims = [color.shape[1], color.shape[0]]
-        color = np.asarray(resize_crop_image(color, list(color_image_dims)))
-        color_image = torch.from_numpy(np.ascontiguousarray(np.transpose(color, [2, 0, 1])).astype(np.float32) / 255.0)
+        raw = np.array(Image.open(color_file))
+        src_wh = [raw.shape[1], raw.shape[0]]
+        rgb = np.asarray(resize_crop_image(raw, list(color_image_dims)))
+        color_t = torch.from_numpy(np.ascontiguousarray(rgb.transpose(2, 0, 1)).astype(np.float32) / 255.0)
         if normalize is not None:
-            color_image = normalize(color_image)
-    if list(color_image_dims) != orig_dims:
-        intrinsic = adjust_intrinsic(intrinsic, orig_dims, list(color_image_dims))
-    return depth_image, color_image, pose, intrinsic
+            color_t = normalize(color_t)
+    if list(color_image_dims) != src_wh:
+        intrinsic = adjust_intrinsic(intrinsic, src_wh, list(color_image_dims))
+    return depth_t, color_t, pose, intrinsic
 
 
 def load_frames(names, world2grids, frame_path, image_path, randomize_frames, depth_image_dims, color_image_dims,
                 color_normalization, load_depth, load_color, max_num_frames=1, pin_memory=False, num_workers=8):
     """Reference signature (data_util.py:862-902) plus ``pin_memory`` (batch tensors in pinned host memory) and
     ``num_workers`` (decoder threads; 0 = decode in the calling thread)."""
-    batch_size = len(names)
-    scenes = [name.split('_room')[0] for name in names]
-    if frame_path == 'self':
-        frames = [[int(name.split('__inc__')[1])] for name in names]
+    B, F = len(names), max_num_frames
+    if frame_path == 'self':  # the chunk's own frame: its id is part of the chunk name
+        frames = [[int(nm.split('__inc__')[1])] for nm in names]
     else:
-        frame_files = [os.path.join(frame_path, name.replace('__inc__', '__cmp__') + '.txt') for name in names]
-        frames = [read_frame_file(frame_file, randomize_frames, max_num_frames) for frame_file in frame_files]
-    if len(frames[0]) < max_num_frames:
+        frames = [read_frame_file(os.path.join(frame_path, nm.replace('__inc__', '__cmp__') + '.txt'), randomize_frames, F)
+                  for nm in names]
+    if len(frames[0]) < F:
         return None, None, None, None, None
-    alloc = (lambda *s: torch.zeros(*s, dtype=torch.float).pin_memory()) if pin_memory else \
-        (lambda *s: torch.zeros(*s, dtype=torch.float))
-    poses, intrinsics = alloc(batch_size, max_num_frames, 4, 4), alloc(batch_size, max_num_frames, 4)
-    depths = alloc(batch_size, max_num_frames, depth_image_dims[1], depth_image_dims[0]) if load_depth else None
-    colors = alloc(batch_size, max_num_frames, 3, color_image_dims[1], color_image_dims[0]) if load_color else None
+    new = (lambda *shape: torch.zeros(*shape, dtype=torch.float).pin_memory()) if pin_memory else \
+        (lambda *shape: torch.zeros(*shape, dtype=torch.float))
+    poses, intrinsics = new(B, F, 4, 4), new(B, F, 4)
+    depths = new(B, F, depth_image_dims[1], depth_image_dims[0]) if load_depth else None
+    colors = new(B, F, 3, color_image_dims[1], color_image_dims[0]) if load_color else None
 
-    def one(bf):
-        b, f = bf
-        fid, scene = frames[b][f], scenes[b]
-        depth_image, color_image, pose, intrinsic = load_frame(
-            os.path.join(image_path, scene + '/depth/' + str(fid) + '.png'),
-            os.path.join(image_path, scene + '/color/' + str(fid) + '.jpg'),
-            os.path.join(image_path, scene + '/camera/' + str(fid) + '.txt'), depth_image_dims, color_image_dims,
-            color_normalization, load_depth, load_color)
-        if load_depth:
-            depths[b, f] = depth_image
-        if load_color:
-            colors[b, f] = color_image
+    def decode(job):
+        b, f = job
+        scene_dir = os.path.join(image_path, names[b].split('_room')[0])
+        fid = str(frames[b][f])
+        d, c, pose, K = load_frame(scene_dir + '/depth/' + fid + '.png', scene_dir + '/color/' + fid + '.jpg',
+                                   scene_dir + '/camera/' + fid + '.txt', depth_image_dims, color_image_dims,
+                                   color_normalization, load_depth, load_color)
+        if d is not None:
+            depths[b, f] = d
+        if c is not None:
+            colors[b, f] = c
         poses[b, f] = pose
-        intrinsics[b, f, 0] = intrinsic[0, 0]
-        intrinsics[b, f, 1] = intrinsic[1, 1]
-        intrinsics[b, f, 2] = intrinsic[0, 2]
-        intrinsics[b, f, 3] = intrinsic[1, 2]
+        intrinsics[b, f] = torch.stack((K[0, 0], K[1, 1], K[0, 2], K[1, 2]))  # fx, fy, mx, my
 
-    work = [(b, f) for b in range(batch_size) for f in range(max_num_frames)]
-    if num_workers and len(work) > 1:
-        list(_executor(num_workers).map(one, work))
+    jobs = [(b, f) for b in range(B) for f in range(F)]
+    if num_workers and len(jobs) > 1:
+        list(_executor(num_workers).map(decode, jobs))
     else:
-        for bf in work:
-            one(bf)
+        for job in jobs:
+            decode(job)
     return depths, colors, poses, intrinsics, frames
