@@ -53,7 +53,9 @@ enum {
     SPSG_FLAG_NO_CLIP = 1u << 0,       /* debug: march every sample like the reference (no ray/box clip)   */
     SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-block skipping                                    */
     SPSG_FLAG_RECORD_HITS = 1u << 2,   /* also write the per-pixel hit voxel index into the workspace       */
-    SPSG_FLAG_GRADS_CLEARED = 1u << 3  /* backward only: rows [0,N) of d_* were cleared by the matching forward */
+    SPSG_FLAG_GRADS_CLEARED = 1u << 3, /* backward only: rows [0,N) of d_* were cleared by the matching forward */
+    SPSG_FLAG_DETERMINISTIC_GRADS = 1u << 4 /* backward, several views per chunk: add a voxel's per-view means in view order
+                                               without float atomics (bit-reproducible; the gather takes ~30 % longer) */
 };
 
 /* Replaces the reference's `opts` CPU tensor [W,H,depth_min,depth_max,thresh,ray_inc,Dx,Dy,Dz]
@@ -146,10 +148,11 @@ SPSG_API int spsg_raycast_forward_indexed(const spsg_raycast_params *p, int32_t 
  *    535-586): d_x[v] = sum over views of mean over the first min(num, max_pixels) pixels registered to
  *    voxel v of grad_x[pixel].  Rows [0, N) of every d_* are fully written (zeros where nothing hit);
  *    rows >= N are left untouched (the reference zero-fills the whole buffer, Python only ever
- *    returns [:N], raycast_rgbd.py:42).  With one view per chunk (the reference's case) the result is written with plain
- *    stores from per-voxel sums accumulated in double precision: no float atomics, bit-identical from run to run.  With
- *    several views per chunk the per-view means of a voxel are added with float atomics (one per view and channel), so the
- *    last bit can vary with their order, like the reference's own atomics (tolerance 1e-3, BASELINE.json). */
+ *    returns [:N], raycast_rgbd.py:42).  Per-voxel sums are accumulated in double precision and rounded once.  With one view
+ *    per chunk (the reference's case) results are written with plain stores: no float atomics, gradients bit-identical from
+ *    run to run.  With several views per chunk the per-view means are added with float atomics (last-bit differences between
+ *    runs, like the reference's own atomics) unless SPSG_FLAG_DETERMINISTIC_GRADS is set, which adds them in view order with
+ *    plain stores. */
 SPSG_API int spsg_raycast_backward(const spsg_raycast_params *p, const float *grad_color, const float *grad_depth,
                                    const float *grad_normal, const float *grad_semantic,
                                    const int32_t *sparse_mapping, const int32_t *mapping3dto2d,

@@ -14,6 +14,7 @@ SPSG_FLAG_NO_CLIP = 1 << 0
 SPSG_FLAG_NO_BRICK_SKIP = 1 << 1
 SPSG_FLAG_RECORD_HITS = 1 << 2
 SPSG_FLAG_GRADS_CLEARED = 1 << 3
+SPSG_FLAG_DETERMINISTIC_GRADS = 1 << 4
 SPSG_LOSS_OUT_FLOATS = 8
 SPSG_DEPTH_MAX_FILL_ROUNDS = 64
 

@@ -149,11 +149,12 @@ __device__ __forceinline__ void pixel_grads_fused(const BackwardArgs &a, const F
 // gradients (independent 8- and 4-byte loads), parks them in shared memory, and lane c then adds column c in
 // registration order (kernel.cu:398-418: mean = sum / count), accumulating in double precision: the registration order
 // depends on which warp's atomic reached a voxel first, and a double sum rounded once gives the same fp32 mean for every
-// order (up to an exact tie).  With one view per chunk the result is written with plain stores, no float atomics.  With several views per chunk the per-view means of a voxel are summed
-// with float atomics onto rows the zero kernel cleared (kAtomic).
+// order (up to an exact tie).  With one view per chunk the result is written with plain stores, no float atomics; with several
+// views see kViews in the loop.
 constexpr int kGatherWarps = 8;
 
-template <bool kFused, bool kAtomic>
+// kViews: 0 = one view per chunk; 1 = several, per-view means added with float atomics (fast); 2 = several, deterministic
+template <bool kFused, int kViews>
 #ifndef SPSG_GATHER_MIN_BLOCKS
 #define SPSG_GATHER_MIN_BLOCKS 8  // 32 registers: full occupancy hides the dependent gathers (the fused variant spills ~150 B and is still faster)
 #endif
@@ -182,45 +183,63 @@ __global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) bac
         const int idx = e.x, img = e.y;
         const int next_item = item + groups_total;
         if (next_item < count) e = a.list[next_item];  // prefetch the next pair
-        const size_t row = (size_t)(img % a.views) * a.num_locs + idx;
-        const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
-        const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
-        const unsigned pixbase = (unsigned)img * P;  // global pixel index < 2^32 / 14 (check_params)
-        const float inv = __frcp_rn((float)max(cnt, 1));
-        double acc0 = 0.0, acc1 = 0.0;  // channels hl and 16 + hl; double: the sum does not depend on the pixel order to fp32 precision
-        for (int k0 = 0; k0 < cnt; k0 += 16) {
-            const int m = min(16, cnt - k0);
-            if (hl < m) {
-                const unsigned gpix = pixbase + (unsigned)__ldg(prow + k0 + hl);
-                if (kFused) {
-                    pixel_grads_fused(a, fc, gpix, tile + hl * 21);
-                } else {
-                    float g[21];
-                    pixel_grads(a, gpix, g);
+        // One view per chunk: the item is the voxel, its mean is written with plain stores.  Several views: the forward listed
+        // one item per (voxel, view) that received pixels.  kViews == 1: every item adds its view's mean with float atomics
+        // onto rows the forward (or the zero kernel) cleared.  kViews == 2 (SPSG_FLAG_DETERMINISTIC_GRADS): the item of the
+        // voxel's LOWEST such view does the whole voxel -- the per-view means added in view order (what F reference calls
+        // accumulated by autograd give), plain stores -- and the others step aside: nothing depends on the order in which
+        // items run, gradients are bit-reproducible, at the price of longer dependent chains (gather +30 % on C3).
+        const int view0 = kViews ? img % a.views : 0, image0 = img - view0;
+        bool owner = true;
+        if (kViews == 2)
+            for (int f = 0; f < view0; f++)
+                if (__ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + idx) > 0) owner = false;
+        if (owner) {
+            float tot0 = 0.0f, tot1 = 0.0f;
+            for (int view = view0; view < (kViews == 2 ? a.views : view0 + 1); view++) {
+                const size_t row = (size_t)view * a.num_locs + idx;
+                const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
+                const int cnt = min(max(__ldg(a.mapping3dto2d_num + row), 0), a.max_pixels);  // kernel.cu:392-393
+                if (cnt == 0) continue;
+                const unsigned pixbase = (unsigned)(image0 + view) * P;  // global pixel index < 2^32 / 14 (check_params)
+                const float inv = __frcp_rn((float)cnt);
+                double acc0 = 0.0, acc1 = 0.0;  // channels hl and 16 + hl; double: the sum does not depend on the pixel order to fp32 precision
+                for (int k0 = 0; k0 < cnt; k0 += 16) {
+                    const int m = min(16, cnt - k0);
+                    if (hl < m) {
+                        const unsigned gpix = pixbase + (unsigned)__ldg(prow + k0 + hl);
+                        if (kFused) {
+                            pixel_grads_fused(a, fc, gpix, tile + hl * 21);
+                        } else {
+                            float g[21];
+                            pixel_grads(a, gpix, g);
 #pragma unroll
-                    for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
+                            for (int c = 0; c < 21; c++) tile[hl * 21 + c] = g[c];
+                        }
+                    }
+                    __syncwarp(hmask);
+                    for (int r = 0; r < m; r++) {
+                        acc0 += (double)tile[r * 21 + hl];
+                        if (hl < 5) acc1 += (double)tile[r * 21 + 16 + hl];
+                    }
+                    __syncwarp(hmask);
                 }
+                tot0 += (float)(acc0 * (double)inv);  // mean = sum / count (kernel.cu:398-418)
+                tot1 += (float)(acc1 * (double)inv);
             }
-            __syncwarp(hmask);
-            for (int r = 0; r < m; r++) {
-                acc0 += (double)tile[r * 21 + hl];
-                if (hl < 5) acc1 += (double)tile[r * 21 + 16 + hl];
+            // channel c -> destination: 0-13 semantic, 14-16 colour, 17 depth->sdf, 18-20 normal
+            float *d0 = hl < 14 ? a.d_semantic + (size_t)idx * 14 + hl : a.d_color + (size_t)idx * 3 + (hl - 14);
+            float *d1 = nullptr;
+            if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
+            else if (hl == 1) d1 = a.d_depth + idx;
+            else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
+            if (kViews == 1) {
+                atomicAdd(d0, tot0);
+                if (d1) atomicAdd(d1, tot1);
+            } else {
+                *d0 = tot0;
+                if (d1) *d1 = tot1;
             }
-            __syncwarp(hmask);
-        }
-        // channel c -> destination: 0-13 semantic, 14-16 colour, 17 depth->sdf, 18-20 normal
-        float *d0 = hl < 14 ? a.d_semantic + (size_t)idx * 14 + hl : a.d_color + (size_t)idx * 3 + (hl - 14);
-        float *d1 = nullptr;
-        if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
-        else if (hl == 1) d1 = a.d_depth + idx;
-        else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
-        const float m0 = (float)(acc0 * (double)inv), m1 = (float)(acc1 * (double)inv);  // mean = sum / count (kernel.cu:398-418)
-        if (kAtomic) {
-            atomicAdd(d0, m0);
-            if (d1) atomicAdd(d1, m1);
-        } else {
-            *d0 = m0;
-            if (d1) *d1 = m1;
         }
         item = next_item;
     }

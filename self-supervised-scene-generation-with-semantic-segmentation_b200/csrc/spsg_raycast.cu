@@ -282,30 +282,32 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + 2 * kGatherWarps - 1) / (2 * kGatherWarps), (long long)sms * 8));
     const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 255) / 256, (long long)sms * 4);
     const bool cleared = (p->flags & SPSG_FLAG_GRADS_CLEARED) != 0;  // the forward's fill pass cleared rows [0, N)
+    const bool multi = p->views_per_chunk > 1, exact = (p->flags & SPSG_FLAG_DETERMINISTIC_GRADS) != 0;
+#define SPSG_GATHER(FUSED, VIEWS, BLOCKS) backward_gather_kernel<FUSED, VIEWS><<<(BLOCKS), kGatherWarps * 32, 0, st>>>(a)
+#define SPSG_GATHER_ANY(BLOCKS)                                                         \
+    do {                                                                                \
+        if (!multi) { if (fused) SPSG_GATHER(true, 0, BLOCKS); else SPSG_GATHER(false, 0, BLOCKS); }       \
+        else if (!exact) { if (fused) SPSG_GATHER(true, 1, BLOCKS); else SPSG_GATHER(false, 1, BLOCKS); }  \
+        else { if (fused) SPSG_GATHER(true, 2, BLOCKS); else SPSG_GATHER(false, 2, BLOCKS); }              \
+    } while (0)
     if (cleared) {
         a.zero_blocks = 0;
         ScopedKernelTimer timer(1, st);
-        if (p->views_per_chunk == 1) {
-            if (fused) backward_gather_kernel<true, false><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-            else backward_gather_kernel<false, false><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-        } else {
-            if (fused) backward_gather_kernel<true, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-            else backward_gather_kernel<false, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-        }
-    } else if (p->views_per_chunk == 1) {
+        SPSG_GATHER_ANY(gather_blocks);
+    } else if (!multi) {
         // one launch: leading CTAs clear the rows of voxels nothing hit, the rest gather (plain stores)
         a.zero_blocks = (int)zero_blocks;
         ScopedKernelTimer timer(1, st);
-        if (fused) backward_gather_kernel<true, false><<<zero_blocks + gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-        else backward_gather_kernel<false, false><<<zero_blocks + gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        SPSG_GATHER_ANY(zero_blocks + gather_blocks);
     } else {
         a.zero_blocks = 0;
         backward_zero_kernel<<<zero_blocks, 256, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         ScopedKernelTimer timer(1, st);
-        if (fused) backward_gather_kernel<true, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
-        else backward_gather_kernel<false, true><<<gather_blocks, kGatherWarps * 32, 0, st>>>(a);
+        SPSG_GATHER_ANY(gather_blocks);
     }
+#undef SPSG_GATHER_ANY
+#undef SPSG_GATHER
     CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
 }

@@ -46,6 +46,7 @@ class RayCastRGBDFunction(Function):
                                   clear_grads=(d_color, d_depth, d_normal, d_semantic) if ctx.grads_cleared else None,
                                   workspace_owner=workspace_owner)
         ctx.workspace_owner = workspace_owner
+        ctx.flags = flags
         ctx.dims = [sparse_mapping.shape[0], dims3d[2], dims3d[1], dims3d[0], num_locs]  # raycast_rgbd.py:30-31
         ctx.views_per_chunk = views_per_chunk
         ctx.save_for_backward(sparse_mapping, mapping3dto2d, mapping3dto2d_num, d_color, d_depth, d_normal,
@@ -62,7 +63,8 @@ class RayCastRGBDFunction(Function):
         raycast_rgbd_cuda.backward(
             grad_color.contiguous(), grad_depth.contiguous(), grad_normal.contiguous(), grad_semantic.contiguous(),
             sparse_mapping, mapping3dto2d, mapping3dto2d_num, ctx.dims, d_color, d_depth, d_normal, d_semantic,
-            views_per_chunk=ctx.views_per_chunk, grads_cleared=ctx.grads_cleared, workspace_owner=ctx.workspace_owner)
+            views_per_chunk=ctx.views_per_chunk, grads_cleared=ctx.grads_cleared, workspace_owner=ctx.workspace_owner,
+            flags=ctx.flags)
         # raycast_rgbd.py:42-43: (locs, vals_sdf, vals_colors, vals_normals, vals_semantic, None...)
         return (None, d_depth[:n], d_color[:n], d_normal[:n], d_semantic[:n]) + \
                (None,) * (len(ctx.needs_input_grad) - 5)
@@ -99,7 +101,7 @@ class RaycastRGBD(nn.Module):
         self.d_normal = torch.zeros(batch_size * max_num_locs_per_sample, 3, device=device)
         self.d_depth = torch.zeros(batch_size * max_num_locs_per_sample, 1, device=device)
         self.d_semantic = torch.zeros(batch_size * max_num_locs_per_sample, 14, device=device)
-        self.flags = 0
+        self.flags = 0  # SPSG_FLAG_* (e.g. _native.SPSG_FLAG_DETERMINISTIC_GRADS for bit-reproducible multi-view gradients)
         # scratch of the native calls (block maps, the backward's work list): owned by the module like the buffers above
         self.workspace = raycast_rgbd_cuda.ModuleWorkspace()
 

@@ -222,7 +222,8 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
 
 
 def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping, mapping3dto2d, mapping3dto2d_num,
-             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1, grads_cleared=False, workspace_owner=None):
+             dims, d_color, d_depth, d_normals, d_semantic, views_per_chunk=1, grads_cleared=False, workspace_owner=None,
+             flags=0):
     """Reference signature (``raycast_color_backward``, raycast_rgbd_cuda.cpp:102-140).
     ``dims`` = int32 CPU tensor (or sequence) [batch, Dx, Dy, Dz, N] (raycast_rgbd.py:30-31)."""
     for t, name in ((grad_color, "grad_color"), (grad_depth, "grad_depth"), (grad_normal, "grad_normal"),
@@ -242,7 +243,7 @@ def backward(grad_color, grad_depth, grad_normal, grad_semantic, sparse_mapping,
                       thresh_sample_dist=0, ray_increment=0, dimx=int(d[1]), dimy=int(d[2]), dimz=int(d[3]),
                       num_chunks=sparse_mapping.shape[0], views_per_chunk=views_per_chunk,
                       max_pixels_per_voxel=mapping3dto2d.shape[1], num_locs=n,
-                      flags=N.SPSG_FLAG_GRADS_CLEARED if grads_cleared else 0)
+                      flags=(N.SPSG_FLAG_GRADS_CLEARED if grads_cleared else 0) | (flags & N.SPSG_FLAG_DETERMINISTIC_GRADS))
     dev = grad_color.device
     px = sparse_mapping.shape[0] * views_per_chunk * p.width * p.height
     if grad_depth.numel() < px or grad_color.numel() < 3 * px or grad_normal.numel() < 3 * px or grad_semantic.numel() < 14 * px:

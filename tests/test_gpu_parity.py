@@ -363,14 +363,20 @@ def test_oversize_input_is_truncated_like_the_reference_wrapper(cuda_device, cap
     assert (out_m[1] != NINF).any()
 
 
-def test_backward_reproduces_bit_for_bit(cuda_device):
-    """One view per chunk: repeated forward + backward passes give bit-identical voxel gradients although the order in which
-    warps register a voxel's pixels (the rows of mapping3dto2d) changes from run to run -- the gather sums in double."""
+@pytest.mark.parametrize("frames", [1, 3])
+def test_backward_reproduces_bit_for_bit(cuda_device, frames):
+    """Repeated forward + backward passes give bit-identical voxel gradients although the order in which warps register a
+    voxel's pixels (the rows of mapping3dto2d) and the order of the work list change from run to run -- the gather sums a
+    voxel's pixels in double and, with several views per chunk and SPSG_FLAG_DETERMINISTIC_GRADS, its per-view means in view
+    order: no float atomics."""
     from spsg_b200 import synthetic as S
     batch, t = scene_tensors([0, 1], cuda_device)
     n = t["locs"].shape[0]
-    _, _, view, intr = views(2, 1, cuda_device, seed=0)
-    mine = _mine(cuda_device, 2, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, n)
+    _, _, view, intr = views(2, frames, cuda_device, seed=0)
+    mine = _mine(cuda_device, 2, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, n, frames=frames)
+    if frames > 1:
+        from spsg_b200 import _native as N
+        mine.flags |= N.SPSG_FLAG_DETERMINISTIC_GRADS
     grads, first = None, None
     for rep in range(4):
         leaves = [t[k].clone().requires_grad_(True) for k in ("sdf", "color", "normal", "semantic")]
