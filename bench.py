@@ -936,8 +936,8 @@ def main():
         secondary("unfused", leg_unfused)
         if args.workload != "c2":
             secondary("c2", leg_c2)
-    # per step: fill, index, cell classes, forward, finalize_loss, gather
-    launches = 6
+    # per step: fill, index, cell classes, forward (its last CTA finalises the loss), gather
+    launches = 5
     if not args.no_train:
         o.mods, o.devsets = None, None
         torch.cuda.empty_cache()

@@ -85,6 +85,8 @@ LossArgs make_loss_args(const spsg_loss_targets *t, double *accum) {
         L.target_label = t->target_label; L.class_weight = t->class_weight; L.voxelsize = t->voxelsize;
     }
     L.accum = accum;
+    L.loss_out = nullptr; L.done = nullptr;
+    if (t) { L.w_depth = t->weight_depth; L.w_color = t->weight_color_loss; L.w_sem = t->weight_semantic; }
     return L;
 }
 
@@ -188,6 +190,8 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         a.guard = std::min(kFracGuard, std::max(ldexpf(1.0f, k - 21), ldexpf(1.0f, -18)));  // 8 ulp of the largest coordinate
     }
     a.loss = make_loss_args(targets, accum);
+    a.loss.loss_out = loss_out;
+    a.loss.done = (int32_t *)(ws + L.head_off) + 16;  // in the per-call zeroed header, next to the list counter
     if (clear_grads && p->num_locs > 0) {  // rows [0, N) of the backward's outputs (kernel.cu:557-560), cleared by the forward's warps
         a.clear = *clear_grads;
         a.clear_rows = p->num_locs;
@@ -231,12 +235,6 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
 #undef SPSG_LAUNCH
     }
     CUDA_TRY(cudaGetLastError());
-    if (targets) {
-        finalize_loss_kernel<<<1, 32, 0, st>>>(accum, loss_out, targets->weight_depth, targets->weight_color_loss,
-                                              targets->weight_semantic, targets->target_depth != nullptr,
-                                              targets->target_color != nullptr, targets->target_label != nullptr);
-        CUDA_TRY(cudaGetLastError());
-    }
     return SPSG_OK;
 }
 
