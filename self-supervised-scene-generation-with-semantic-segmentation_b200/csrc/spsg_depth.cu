@@ -71,51 +71,79 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict_
 // median_fill_depthmap_kernel (dkernel.cu:89-140).  Valid pixels are copied.  A hole takes the order statistic the
 // reference reads out of its sorted 11x11 window: the ((n+1)/2)-th smallest (0-based) of the n valid values, each
 // quantised to millimetres as (int)(1000 d + 0.5f).  (For n < 2 the reference indexes past its array; here: 0.)
+// The reference bubble-sorts 121 values per hole in one thread; here a warp (32 pixels of a row) handles its holes one
+// after the other TOGETHER: the lanes load the window into shared memory (4 values each), every lane ranks its own four
+// candidates against all 121 (broadcast reads), and the lane whose candidate has the wanted rank publishes it -- a chain
+// of ~500 steps per hole instead of ~15 000 in the thread that owns it.
 // `gate` (may be NULL): the pass does nothing when *gate == 0.  `holes_out` (may be NULL): counts the zeros written.
 __global__ void __launch_bounds__(256) median_fill_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
                                                           int height, const int32_t *gate, int32_t *holes_out) {
     if (gate && *gate == 0) return;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    __shared__ int s_win[8][128];
+    const unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + warp;
     const float *img = in + (size_t)blockIdx.z * width * height;
-    bool hole = false;
-    if (x < width && y < height) {
-        const float cur = img[y * width + x];
-        float result = cur;
-        if (!depth_valid(cur)) {
-            int vals[kFillCells];
-            int n = 0;
-            for (int i = -kFillRadius; i <= kFillRadius; i++)
-                for (int j = -kFillRadius; j <= kFillRadius; j++) {
-                    const int xx = x + j, yy = y + i;
-                    if (xx >= 0 && xx < width && yy >= 0 && yy < height) {
-                        const float d = img[yy * width + xx];
-                        if (depth_valid(d)) vals[n++] = (int)(1000 * d + 0.5f);
-                    }
-                }
-            int val = 0;
-            if (n >= 2) {
-                const int k = (n + 1) / 2;  // rank among the valid values, ascending
-                for (int i = 0; i < n; i++) {
-                    const int v = vals[i];
-                    int less = 0, equal = 0;
-                    for (int j = 0; j < n; j++) {
-                        less += vals[j] < v;
-                        equal += vals[j] == v;
-                    }
-                    if (less <= k && k < less + equal) {
-                        val = v;
-                        break;
-                    }
+    const bool inside = x < width && y < height;
+    const float cur = inside ? img[y * width + x] : 1.0f;
+    float result = cur;
+    int *win = s_win[warp];
+    unsigned todo = __ballot_sync(kFull, inside && !depth_valid(cur));
+    while (todo) {
+        const int h = __ffs(todo) - 1;  // the hole lane served now: pixel (hx, y)
+        todo &= todo - 1;
+        const int hx = blockIdx.x * 32 + h;
+        int mine[4];
+        int n = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int e = lane + 32 * r;  // window element (row i, column j), row-major like the reference
+            int q = -1;
+            if (e < kFillCells) {
+                const int xx = hx + e % kFillDiameter - kFillRadius, yy = y + e / kFillDiameter - kFillRadius;
+                if (xx >= 0 && xx < width && yy >= 0 && yy < height) {
+                    const float d = img[yy * width + xx];
+                    if (depth_valid(d)) q = (int)(1000 * d + 0.5f);
                 }
             }
-            result = val <= 0 ? 0.0f : 0.001f * (float)val;
+            mine[r] = q;
+            win[e] = q;
+            // (a valid depth can quantise to a non-positive value only if it is below 0.5 mm or negative; such entries stay
+            // in the ranking, exactly as in the reference's array)
+            n += __popc(__ballot_sync(kFull, e < kFillCells && q != -1 ? true : false));
         }
+        __syncwarp();
+        int val = 0;
+        if (n >= 2) {
+            const int k = (n + 1) / 2;  // rank among the valid values, ascending
+            int found = 0, fv = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int v = mine[r];
+                int less = 0, equal = 0;
+                if (v != -1) {
+                    for (int j = 0; j < kFillCells; j++) {
+                        const int w = win[j];
+                        less += (w != -1) & (w < v);
+                        equal += w == v;
+                    }
+                    if (less <= k && k < less + equal) { found = 1; fv = v; }
+                }
+            }
+            const unsigned who = __ballot_sync(kFull, found);
+            val = __shfl_sync(kFull, fv, who ? __ffs(who) - 1 : 0);  // every lane that found it holds the same value
+        }
+        if (lane == h) result = val <= 0 ? 0.0f : 0.001f * (float)val;
+        __syncwarp();
+    }
+    bool hole = false;
+    if (inside) {
         out[(size_t)blockIdx.z * width * height + y * width + x] = result;
         hole = result == 0.0f;
     }
     if (holes_out) {
-        const unsigned m = __ballot_sync(0xffffffffu, hole);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(holes_out, __popc(m));
+        const unsigned m = __ballot_sync(kFull, hole);
+        if (lane == 0 && m) atomicAdd(holes_out, __popc(m));
     }
 }
 
