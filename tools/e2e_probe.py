@@ -1,33 +1,47 @@
-"""Development aid: where the end-to-end step of bench.py spends its time -- the host->device copy alone, the
-render + losses + backward alone (inputs already in the device slots), and both (what bench.py reports as e2e).
-Runs under torchrun too (every rank probes its own GPU at the same time; max over ranks is printed)."""
+"""Development aid: the two halves of bench.py's end-to-end step, timed alone -- (a) the host -> device copy of one packed
+pinned input set, (b) the public API path (render_with_2d_losses + backward) with the inputs already in HBM.
+usage: python tools/e2e_probe.py [--c2]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-import torch.distributed as dist
 import bench
 
-args = bench.parse_args()
-rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
-dev = torch.device("cuda", local)
+dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
-if rank == 0:
-    print("cpus: os.cpu_count=%d affinity=%d" % (os.cpu_count(), len(os.sched_getaffinity(0))))
-    try:
-        nodes = sorted(d for d in os.listdir("/sys/devices/system/node") if d.startswith("node"))
-        print("numa nodes:", nodes, [open("/sys/devices/system/node/%s/cpulist" % n).read().strip() for n in nodes])
-    except OSError as e:
-        print("numa: n/a", e)
-    os.system("nvidia-smi topo -m 2>/dev/null | head -14 | cut -c1-150")
-B, F = (1, 1) if args.workload == "c2" else (8, 5)
-ctx = bench.run_ours(args, dev, rank, B, F, args.sets or 4)
-nbytes = bench.bytes_of(ctx["host"][0], bench.H2D_KEYS)
-for mode in ("copy", "compute", "full", "copy", "compute", "full"):
-    ms, _ = bench.e2e_ours(ctx, dev, world, 60, 5, mode=mode)
-    if rank == 0:
-        print("%-8s %.1f us/step  (%.1f GB/s of input per rank)" % (mode, ms / 60 * 1e3, nbytes / (ms / 60 * 1e-3) / 1e9))
-if world > 1:
-    dist.destroy_process_group()
+B, F = (1, 1) if "--c2" in sys.argv else (8, 5)
+o = bench.Ours(dev, 0, B, F, 2)
+S = o.S
+
+
+def timed(fn, n=40, warm=5):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+packed = [bench.pack_host(h) for h in o.host]
+slot = torch.empty(max(b.numel() for b, _ in packed), dtype=torch.uint8, device=dev)
+copy_ms = timed(lambda i: slot[:packed[i % 2][0].numel()].copy_(packed[i % 2][0], non_blocking=True))
+
+
+def api(i):
+    d = o.devsets[i % 2]
+    leaves = [d[k].detach().requires_grad_(True) for k in ("sdf", "color", "semantic")]
+    total, _, _ = o.render(o.mods[i % 2], d["locs"], leaves[0], leaves[1], d["normal"], leaves[2], d["view"], d["intr"],
+                           images_depth=d["t_depth"], images_color=d["t_color"], target2d_label=d["t_label"],
+                           weight_semantic_class=o.cw, voxelsize=S.VOXELSIZE)
+    total.backward()
+
+
+api_ms = timed(api)
+nbytes = packed[0][0].numel()
+print("B=%d F=%d: copy of %.1f MB alone %.3f ms (%.1f GB/s); API path with resident inputs %.3f ms"
+      % (B, F, nbytes / 1e6, copy_ms, nbytes / copy_ms / 1e6, api_ms))
