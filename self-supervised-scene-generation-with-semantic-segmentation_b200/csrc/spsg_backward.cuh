@@ -152,6 +152,10 @@ __device__ __forceinline__ void pixel_grads_fused(const BackwardArgs &a, const F
 // order (up to an exact tie).  With one view per chunk the result is written with plain stores, no float atomics; with several
 // views see kViews in the loop.
 constexpr int kGatherWarps = 8;
+#ifndef SPSG_GATHER_GROUP
+#define SPSG_GATHER_GROUP 16
+#endif
+constexpr int kGatherGroup = SPSG_GATHER_GROUP;  // lanes per (voxel, view) item
 
 // kViews: 0 = one view per chunk; 1 = several, per-view means added with float atomics (fast); 2 = several, deterministic
 template <bool kFused, int kViews>
@@ -163,16 +167,17 @@ __global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) bac
         zero_rows<true>(a, ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, ((long long)a.zero_blocks * blockDim.x) >> 5);
         return;
     }
-    // half a warp per item: 16 lanes cover the typical pixel count of a voxel, the two halves work on different items
-    __shared__ float s_g[kGatherWarps * 2][16 * 21];
+    // kGatherGroup lanes per item, 32 / kGatherGroup items in flight per warp: the groups work on different items
+    constexpr int G = kGatherGroup, kPerWarp = 32 / G, kSlots = (21 + G - 1) / G;
+    __shared__ float s_g[kGatherWarps * kPerWarp][G * 21];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int hl = lane & 15, half = lane >> 4;
-    const unsigned hmask = 0xffffu << (16 * half);
-    float *tile = s_g[warp * 2 + half];
-    const int groups_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps * 2;
+    const int hl = lane & (G - 1), half = lane / G;
+    const unsigned hmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * half);
+    float *tile = s_g[warp * kPerWarp + half];
+    const int groups_total = (int)(gridDim.x - a.zero_blocks) * kGatherWarps * kPerWarp;
     const int count = *a.list_count;
     const unsigned P = (unsigned)(a.width * a.height);
-    int item = (((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp) * 2 + half;
+    int item = (((int)blockIdx.x - a.zero_blocks) * kGatherWarps + warp) * kPerWarp + half;
     int2 e = item < count ? a.list[item] : make_int2(0, 0);
     FusedCoef fc = {0.0f, 0.0f, 0.0f};
     if (kFused) fc = fused_coef(a);
@@ -195,7 +200,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) bac
             for (int f = 0; f < view0; f++)
                 if (__ldg(a.mapping3dto2d_num + (size_t)f * a.num_locs + idx) > 0) owner = false;
         if (owner) {
-            float tot0 = 0.0f, tot1 = 0.0f;
+            float tot[kSlots];
+#pragma unroll
+            for (int j = 0; j < kSlots; j++) tot[j] = 0.0f;
             for (int view = view0; view < (kViews == 2 ? a.views : view0 + 1); view++) {
                 const size_t row = (size_t)view * a.num_locs + idx;
                 const int32_t *prow = a.mapping3dto2d + row * a.max_pixels;
@@ -203,9 +210,11 @@ __global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) bac
                 if (cnt == 0) continue;
                 const unsigned pixbase = (unsigned)(image0 + view) * P;  // global pixel index < 2^32 / 14 (check_params)
                 const float inv = __frcp_rn((float)cnt);
-                double acc0 = 0.0, acc1 = 0.0;  // channels hl and 16 + hl; double: the sum does not depend on the pixel order to fp32 precision
-                for (int k0 = 0; k0 < cnt; k0 += 16) {
-                    const int m = min(16, cnt - k0);
+                double acc[kSlots];  // channels hl + G j; double: the sum does not depend on the pixel order to fp32 precision
+#pragma unroll
+                for (int j = 0; j < kSlots; j++) acc[j] = 0.0;
+                for (int k0 = 0; k0 < cnt; k0 += G) {
+                    const int m = min(G, cnt - k0);
                     if (hl < m) {
                         const unsigned gpix = pixbase + (unsigned)__ldg(prow + k0 + hl);
                         if (kFused) {
@@ -219,26 +228,26 @@ __global__ void __launch_bounds__(kGatherWarps * 32, SPSG_GATHER_MIN_BLOCKS) bac
                     }
                     __syncwarp(hmask);
                     for (int r = 0; r < m; r++) {
-                        acc0 += (double)tile[r * 21 + hl];
-                        if (hl < 5) acc1 += (double)tile[r * 21 + 16 + hl];
+#pragma unroll
+                        for (int j = 0; j < kSlots; j++)
+                            if (hl + G * j < 21) acc[j] += (double)tile[r * 21 + hl + G * j];
                     }
                     __syncwarp(hmask);
                 }
-                tot0 += (float)(acc0 * (double)inv);  // mean = sum / count (kernel.cu:398-418)
-                tot1 += (float)(acc1 * (double)inv);
+#pragma unroll
+                for (int j = 0; j < kSlots; j++) tot[j] += (float)(acc[j] * (double)inv);  // mean = sum / count (kernel.cu:398-418)
             }
             // channel c -> destination: 0-13 semantic, 14-16 colour, 17 depth->sdf, 18-20 normal
-            float *d0 = hl < 14 ? a.d_semantic + (size_t)idx * 14 + hl : a.d_color + (size_t)idx * 3 + (hl - 14);
-            float *d1 = nullptr;
-            if (hl == 0) d1 = a.d_color + (size_t)idx * 3 + 2;
-            else if (hl == 1) d1 = a.d_depth + idx;
-            else if (hl < 5) d1 = a.d_normal + (size_t)idx * 3 + (hl - 2);
-            if (kViews == 1) {
-                atomicAdd(d0, tot0);
-                if (d1) atomicAdd(d1, tot1);
-            } else {
-                *d0 = tot0;
-                if (d1) *d1 = tot1;
+#pragma unroll
+            for (int j = 0; j < kSlots; j++) {
+                const int c = hl + G * j;
+                if (c < 21) {
+                    float *d = c < 14 ? a.d_semantic + (size_t)idx * 14 + c
+                             : c < 17 ? a.d_color + (size_t)idx * 3 + (c - 14)
+                             : c == 17 ? a.d_depth + idx : a.d_normal + (size_t)idx * 3 + (c - 18);
+                    if (kViews == 1) atomicAdd(d, tot[j]);
+                    else *d = tot[j];
+                }
             }
         }
         item = next_item;

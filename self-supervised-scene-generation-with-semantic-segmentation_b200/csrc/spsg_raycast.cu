@@ -277,7 +277,7 @@ int launch_backward(const spsg_raycast_params *p, bool fused, const float *g_or_
     const int sms = sm_count();
     // half a warp per listed (voxel, view) pair; the list length is only known on the device: size for its bound N * F
     const long long max_items = p->num_locs * p->views_per_chunk;
-    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + 2 * kGatherWarps - 1) / (2 * kGatherWarps), (long long)sms * 8));
+    const unsigned gather_blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_items + (32 / kGatherGroup) * kGatherWarps - 1) / ((32 / kGatherGroup) * kGatherWarps), (long long)sms * 8));
     const unsigned zero_blocks = (unsigned)std::min<long long>((p->num_locs + 255) / 256, (long long)sms * 4);
     const bool cleared = (p->flags & SPSG_FLAG_GRADS_CLEARED) != 0;  // the forward's fill pass cleared rows [0, N)
     const bool multi = p->views_per_chunk > 1, exact = (p->flags & SPSG_FLAG_DETERMINISTIC_GRADS) != 0;
