@@ -64,7 +64,10 @@ class ViewGuidedTrainStep:
         return losses.labels_from_render(raycast_semantic)  # (I,H,W) uint8, 14 = miss / unlabeled
 
     def _render_input(self, inputs, view_matrix, intrinsics, transform):
-        """train.py:556-578: the input scan's colour / normal rendering (the discriminator's conditioning)."""
+        """train.py:556-578: the input scan's colour / normal rendering (the discriminator's conditioning; nothing else reads it,
+        so with the GAN term off it only keeps the step's work like the reference's).  Its normals come from the sparse
+        normals kernel (absent neighbours count as 0), where the reference uses `loss.compute_normals` on the dense input
+        volume (truncated neighbours count as +-truncation): the two differ at the rim of the input's band."""
         locs, vals, cols = sparsify.sparsify_predictions(inputs[:, :1].contiguous(), self.truncation, None,
                                                          inputs[:, 1:4].contiguous())
         input_normals = normals.compute_normals_sparse(locs, vals, self.dims3d, transform=transform)
