@@ -54,6 +54,8 @@ enum {
     SPSG_FLAG_NO_BRICK_SKIP = 1u << 1, /* debug: no empty-block skipping                                    */
     SPSG_FLAG_RECORD_HITS = 1u << 2,   /* also write the per-pixel hit voxel index into the workspace       */
     SPSG_FLAG_GRADS_CLEARED = 1u << 3, /* backward only: rows [0,N) of d_* were cleared by the matching forward */
+    SPSG_FLAG_SMEM_MAPS = 1u << 5,     /* debug: march maps staged in shared memory (TMA) even for several chunks          */
+    SPSG_FLAG_GLOBAL_MAPS = 1u << 6,   /* debug: march maps read through L1 + one global tile counter even for one chunk   */
     SPSG_FLAG_DETERMINISTIC_GRADS = 1u << 4 /* backward, several views per chunk: add a voxel's per-view means in view order
                                                without float atomics (bit-reproducible; the gather takes ~30 % longer) */
 };

@@ -15,6 +15,8 @@ SPSG_FLAG_NO_BRICK_SKIP = 1 << 1
 SPSG_FLAG_RECORD_HITS = 1 << 2
 SPSG_FLAG_GRADS_CLEARED = 1 << 3
 SPSG_FLAG_DETERMINISTIC_GRADS = 1 << 4
+SPSG_FLAG_SMEM_MAPS = 1 << 5
+SPSG_FLAG_GLOBAL_MAPS = 1 << 6
 SPSG_LOSS_OUT_FLOATS = 8
 SPSG_DEPTH_MAX_FILL_ROUNDS = 64
 

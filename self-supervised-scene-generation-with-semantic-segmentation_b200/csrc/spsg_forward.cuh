@@ -206,13 +206,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
     __shared__ int s_next_chunk;
     int own_next = blockIdx.x % a.num_chunks, steal_k = 0;
     for (bool first_chunk = true;; first_chunk = false) {
-        if (own_next >= a.num_chunks && a.num_chunks == 1) break;  // a single chunk: nothing to steal
+        // Maps read through L1 (!kSmemMaps): nothing ties a CTA to a chunk, so there is one pass in which every warp takes
+        // tiles of ALL chunks from one global counter (chunk-major order: the SMs work on the same one or two chunks at
+        // any time, which keeps their maps and bricks in L1 / L2) -- no election, no block-level barrier, no tail behind a
+        // chunk switch.
+        if (!kSmemMaps && !first_chunk) break;
+        if (own_next >= a.num_chunks && a.num_chunks == 1 && kSmemMaps) break;  // a single chunk: nothing to steal
         if (!first_chunk) {
             __syncthreads();  // all warps are done reading the maps before the next chunk's copy overwrites them
             if (kSmemMaps) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         int code = -1;
-        if (own_next < a.num_chunks) {
+        if (!kSmemMaps) {
+            code = 1;  // placeholder chunk 0: the chunk follows from the tile, see bind_chunk
+        } else if (own_next < a.num_chunks) {
             code = own_next * 2 + 1;  // (every thread knows: no election)
         } else {
             if (warp == 0) {
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
             code = s_next_chunk;
         }
         if (code < 0) break;
-        const int chunk = code >> 1;
+        int chunk = code >> 1;
         const bool own = (code & 1) != 0;
         if (own) own_next += (int)gridDim.x;
         if (kSmemMaps) {
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                 bulk_copy_g2s(s_bmap, a.bmap + (size_t)chunk * a.bpc, bm_bytes, mbar);
             }
         }
-        const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;
+        const uint2 *vbits = kSmemMaps ? s_vbits : a.vbits + (size_t)chunk * a.vpc;   // (re-bound per tile in global mode)
         const uint8_t *bmap = kSmemMaps ? s_bmap : a.bmap + (size_t)chunk * a.bpc;
         Volume v;
         v.index = a.sparse_mapping;
@@ -269,16 +276,27 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
         // CTAs that share this chunk: ranks 0..group-1.  First round static and contiguous per CTA, then dynamic.
         const int nb = a.num_chunks;
         const int group = chunk < (int)gridDim.x ? ((int)gridDim.x - 1 - chunk) / nb + 1 : 1, rank = blockIdx.x / nb;
-        const int static_tiles = min(total_tiles, group * kWarps);
+        // (global mode: no static round, `tile` runs over the tiles of all chunks)
+        const int tile_limit = kSmemMaps ? total_tiles : total_tiles * nb;
+        const int static_tiles = kSmemMaps ? min(total_tiles, group * kWarps) : 0;
         const int per = static_tiles / group, extra = static_tiles - per * group;
-        const int my_first = rank * per + min(rank, extra), my_count = own ? per + (rank < extra ? 1 : 0) : 0;
-        int tile = warp < my_count ? my_first + warp : total_tiles;
-        int32_t *counter = a.tile_counter + chunk;
-        if (tile >= total_tiles && static_tiles < total_tiles) {
+        const int my_first = rank * per + min(rank, extra), my_count = (own && kSmemMaps) ? per + (rank < extra ? 1 : 0) : 0;
+        int tile = warp < my_count ? my_first + warp : tile_limit;
+        int32_t *counter = a.tile_counter + (kSmemMaps ? chunk : 0);
+        if (tile >= tile_limit && static_tiles < tile_limit) {
             int t = 0;
             if (lane == 0) t = static_tiles + atomicAdd(counter, 1);
             tile = __shfl_sync(kFull, t, 0);
         }
+        // global mode: the chunk of a tile, its volume and maps; returns the tile's index within the chunk
+        auto bind_chunk = [&](int t) -> int {
+            if (kSmemMaps) return t;
+            chunk = t / total_tiles;
+            v.cell0 = (unsigned)chunk * (unsigned)cells;
+            vbits = a.vbits + (size_t)chunk * a.vpc;
+            bmap = a.bmap + (size_t)chunk * a.bpc;
+            return t - chunk * total_tiles;
+        };
 
         // Per-lane ray of the warp's current tile: set up (and clipped against the grid) before the chunk's maps are needed,
         // so that the first tile's set-up overlaps the TMA copies.
@@ -379,12 +397,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
         };
         TileRay q;
         q.inside = false;
-        if (tile < total_tiles) prepare(tile, q);
+        if (tile < tile_limit) prepare(bind_chunk(tile), q);
         if (kSmemMaps) mbar_wait(mbar, phase);  // the chunk's class planes and block map have landed
 
-        while (tile < total_tiles) {
-            int next = total_tiles;
-            if (lane == 0 && static_tiles < total_tiles) next = static_tiles + atomicAdd(counter, 1);  // prefetched
+        while (tile < tile_limit) {
+            int next = tile_limit;
+            if (lane == 0 && static_tiles < tile_limit) next = static_tiles + atomicAdd(counter, 1);  // prefetched
             if (q.inside) {
                 const Ray r = q.r;
                 const float invx = q.invx, invy = q.invy, invz = q.invz, kx = q.kx, ky = q.ky, kz = q.kz;
@@ -736,7 +754,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
 #endif
             }
             tile = __shfl_sync(kFull, next, 0);
-            if (tile < total_tiles) prepare(tile, q);
+            if (tile < tile_limit) prepare(bind_chunk(tile), q);
         }
         if (kSmemMaps) phase ^= 1u;
     }

@@ -81,6 +81,33 @@ def test_skipping_is_observationally_identical(cuda_device, flags):
     assert torch.equal(a.mapping3dto2d_num[:n], b.mapping3dto2d_num[:n])
 
 
+@pytest.mark.parametrize("chunks,frames", [(1, 1), (3, 2)])
+def test_map_placement_paths_agree_bit_for_bit(cuda_device, chunks, frames):
+    """The two homes of the march maps -- TMA-staged shared memory with chunk-bound CTAs (default for one chunk) and L1 with
+    one global tile counter (default for several) -- render identical images and register identical pixel counts, and both
+    equal the reference."""
+    from spsg_b200 import _native as N
+    from spsg_b200 import synthetic as S
+    w, h = 160, 128
+    batch, t = scene_tensors(list(range(30, 30 + chunks)), cuda_device)
+    n = t["locs"].shape[0]
+    _, _, view, intr = views(chunks, frames, cuda_device, seed=6, width=w, height=h)
+    outs, nums = [], []
+    for flag in (N.SPSG_FLAG_SMEM_MAPS, N.SPSG_FLAG_GLOBAL_MAPS):
+        m = _mine(cuda_device, chunks, S.DIMS_ZYX, w, h, n, frames=frames)
+        m.flags = flag
+        outs.append([o.clone() for o in m(t["locs"], t["sdf"], t["color"], t["normal"], t["semantic"], view, intr)])
+        nums.append(m.mapping3dto2d_num[:n * frames].clone())
+    _assert_render_equal(outs[0], outs[1], "smem vs global maps")
+    assert torch.equal(nums[0], nums[1])
+    ref = _ref(cuda_device, chunks, S.DIMS_ZYX, w, h, n)
+    for f in range(frames):
+        sel = torch.arange(chunks, device=cuda_device) * frames + f
+        out_r = ref.forward(t["locs"], t["sdf"], t["color"], t["normal"], t["semantic"], view[sel].contiguous(), intr[sel].contiguous())
+        for a, b in zip(outs[1], out_r):
+            assert count_bit_mismatch(a[sel], b) == 0
+
+
 @pytest.mark.parametrize("inc,dmin,thresh", [(0.3, 5.0, None), (1.7, 0.0, None), (0.123, 20.0, None),
                                              (0.75, 5.0, None), (0.9, 5.0, 1.5), (1.0, 3.0, 0.4)])
 def test_forward_bit_exact_march_parameters(cuda_device, inc, dmin, thresh):
