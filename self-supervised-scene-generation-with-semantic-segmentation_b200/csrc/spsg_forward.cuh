@@ -10,7 +10,7 @@
 #ifdef SPSG_STATS
 // development build only (-DSPSG_STATS): event counters of the march, read back with spsg_debug_stats()
 __device__ unsigned long long g_stats[48];
-__device__ int g_tile_stats[8192][8];  // per tile: total, setup, march, refine, epilogue cycles, iterations, smid, start
+__device__ int g_tile_stats[131072][8];  // per tile: total, setup, march, refine, epilogue cycles, iterations, smid, start
 #define STAT_MAX(k, v) atomicMax(&g_stats[k], (unsigned long long)(v))
 #define STAT_ADD(k, v) atomicAdd(&g_stats[k], (unsigned long long)(v))
 #if SPSG_STATS == 1
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) raycast_forward_kernel(const F
                     STAT_ADD(44, clk3 - clk_e2); STAT_MAX(45, clk3 - clk_e2);    // staging + stores
                     STAT_ADD(24, clk3 - clk0); STAT_MAX(25, clk3 - clk0);        // whole tile
                     STAT_MAX(26, my_iters);
-                    if (tile < 8192) {
+                    if (tile < 131072) {
                         unsigned smid;
                         asm("mov.u32 %0, %%smid;" : "=r"(smid));
                         int *ts = g_tile_stats[tile];

@@ -326,7 +326,7 @@ extern "C" {
 
 #ifdef SPSG_STATS
 SPSG_API int spsg_debug_tile_stats(int *out) {
-    return cudaMemcpyFromSymbol(out, g_tile_stats, sizeof(int) * 8192 * 8) == cudaSuccess ? SPSG_OK : SPSG_ERR_CUDA;
+    return cudaMemcpyFromSymbol(out, g_tile_stats, sizeof(int) * 131072 * 8) == cudaSuccess ? SPSG_OK : SPSG_ERR_CUDA;
 }
 
 SPSG_API int spsg_debug_stats(unsigned long long *out, int reset) {

@@ -16,9 +16,9 @@ for rep in range(3):
     with torch.no_grad():
         out = m(t["locs"], t["sdf"], t["color"], t["normal"], t["semantic"], view, intr)
     torch.cuda.synchronize()
-buf = (ctypes.c_int * (8192 * 8))()
+buf = (ctypes.c_int * (131072 * 8))()
 N.lib.spsg_debug_tile_stats(buf)
-a = np.frombuffer(buf, dtype=np.int32).reshape(8192, 8)[:2560]
+a = np.frombuffer(buf, dtype=np.int32).reshape(131072, 8)[:2560]
 hit = (out[1][0] != -float("inf")).cpu().numpy()
 order = np.argsort(-a[:, 0])
 print("tile  total  setup  march refine epilog iters smid  start | hits")
