@@ -320,7 +320,17 @@ class Ours:
             for i in range(n):
                 step(i, i == n - 1)
 
-        return e2e_protocol(run, steps, warmup, dev, world), float(result)
+        ms = e2e_protocol(run, steps, warmup, dev, world)
+
+        # The same bytes with nothing behind them: every rank copies its packed buffer at the same time (max over ranks).
+        # e2e above cannot be faster than this; with several GPUs it shows what the host's memory system and PCIe
+        # topology give each GPU when all of them pull at once.
+        def copies(n):
+            for i in range(n):
+                buf = packed[i % num_sets][0]
+                slots[i % 2][:buf.numel()].copy_(buf, non_blocking=True)
+        ms_copy = e2e_protocol(copies, 10, 3, dev, world) / 10
+        return ms, float(result), {"ms_per_step": ms_copy, "gb_per_s_per_gpu": packed[0][0].numel() / (ms_copy * 1e-3) / 1e9}
 
     def e2e_device_flow(self, world, steps, warmup):
         """The training data flow: the voxel tensors never come from the host -- the generator leaves dense heads (SDF,
@@ -894,7 +904,7 @@ def main():
     sampler.stop_flag = True
     value = world * o.rays * steps / (ms * 1e-3)
     e2e_steps = max(10, min(args.steps, 60))
-    ms_e2e, last_loss = o.e2e(world, e2e_steps, min(args.warmup, 5))
+    ms_e2e, last_loss, copy_only = o.e2e(world, e2e_steps, min(args.warmup, 5))
     e2e = world * o.rays * e2e_steps / (ms_e2e * 1e-3)
     roof = o.roofline(min(args.steps, 40), fused=True) if rank == 0 else None
     extra = {}
@@ -949,7 +959,9 @@ def main():
                          "api": "spsg_b200.losses.render_with_2d_losses (fused raycast + depth/colour/semantic losses) "
                                 "+ backward; every step's inputs copied from one packed pinned-host buffer on a copy stream "
                                 "(double-buffered); median of %d timed regions" % E2E_REPEATS,
-                         "last_loss": last_loss},
+                         "last_loss": last_loss,
+                         "h2d_copy_only": dict(copy_only, note="the step's pinned host -> device copy alone, all ranks at once: "
+                                                               "the floor of this leg on this host")},
                     gpu_launches=launches * steps, roofline=roof, **extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_raycast_baseline()

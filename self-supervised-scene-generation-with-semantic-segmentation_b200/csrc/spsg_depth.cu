@@ -6,11 +6,15 @@
 // Same arithmetic as the reference, expression by expression (float / double mix of the two Gaussians included), so that
 // the results can be compared bit for bit with the compiled reference extension.  What changes is the shape of the work:
 //   * depth -> camera space -> normals is one kernel (the camera-space image is still written: callers can read it);
-//   * the median hole fill selects the reference's order statistic by rank counting instead of a 121-element bubble
-//     sort in local memory, and only for hole pixels;
-//   * the fill iterations terminate on the device: every fill pass counts the holes it leaves and the following passes
-//     return at once when that count is zero, so the whole pipeline is enqueued without a host round trip per iteration
-//     (the reference synchronises on `(depth == 0).any()` up to 21 times, depth_utils.py:86-92).
+//   * the median hole fill selects the reference's order statistic by a warp-wide radix select instead of a 121-element
+//     bubble sort in local memory, and only for hole pixels;
+//   * the fill iterations terminate on the device: every fill pass counts the holes it leaves, so the whole pipeline is
+//     enqueued without a host round trip per iteration (the reference synchronises on `(depth == 0).any()` up to 21
+//     times, depth_utils.py:86-92);
+//   * the fill rounds and the normals are ONE cooperative launch (fill_rounds_normals_kernel): passes of a grid-resident
+//     kernel separated by grid barriers, and the fill loop simply ends when a round leaves no hole (the launch-per-pass
+//     form, with passes that return at once, remains for devices without cooperative launch).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -29,16 +33,32 @@ constexpr int kFillCells = kFillDiameter * kFillDiameter;
 
 __device__ __forceinline__ bool depth_valid(float d) { return d != -CUDART_INF_F && d != 0.0f; }
 
-// bilateral_filter_floatmap_kernel (dkernel.cu:41-86); also counts the holes of the input (zero pixels) into *holes.
-__global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
-                                                        int height, float sigmaD, float sigmaR, int32_t *holes) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const float *img = in + (size_t)blockIdx.z * width * height;
+constexpr int kTableRadius = 8;  // spatial Gaussian table: windows up to 17x17 (the training step uses 9x9)
+constexpr int kTableDiameter = 2 * kTableRadius + 1;
+
+// gaussD (dkernel.cu:16-19) of every window offset, once per CTA: the expression of the per-tap form below, so the
+// values are the same floats.
+__device__ __forceinline__ void spatial_table_fill(float *table, float sigmaD, int radius) {
+    if (radius > kTableRadius) return;
+    for (int e = threadIdx.x; e < kTableDiameter * kTableDiameter; e += blockDim.x) {
+        const int dx = e / kTableDiameter - kTableRadius, dy = e % kTableDiameter - kTableRadius;
+        table[e] = exp(-((dx * dx + dy * dy) / (2.0f * sigmaD * sigmaD)));
+    }
+}
+
+// bilateral_filter_floatmap_kernel (dkernel.cu:41-86) for the 32x8-pixel tile (bx, by) of frame bz; also counts the holes
+// of the input (zero pixels) into *holes.
+__device__ __forceinline__ void bilateral_tile(const float *__restrict__ in, float *__restrict__ out, int width, int height,
+                                               float sigmaD, float sigmaR, int32_t *holes, int bx, int by, int bz,
+                                               const float *table) {
+    const int x = bx * 32 + (threadIdx.x & 31), y = by * 8 + (threadIdx.x >> 5);
+    const float *img = in + (size_t)bz * width * height;
     const bool inside = x < width && y < height;
     float result = 0.0f;
     bool hole = false;
     if (inside) {
         const int radius = (int)ceil(2.0 * sigmaD);  // dkernel.cu:56
+        const bool tabled = radius <= kTableRadius;
         const float center = img[y * width + x];
         hole = center == 0.0f;
         if (depth_valid(center)) {
@@ -51,7 +71,8 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict_
                             const int dx = m - x, dy = n - y;
                             const float dist = cur - center;
                             // gaussD in float, gaussR through double, exactly as written at dkernel.cu:16-29
-                            const float gd = exp(-((dx * dx + dy * dy) / (2.0f * sigmaD * sigmaD)));
+                            const float gd = tabled ? table[(dx + kTableRadius) * kTableDiameter + dy + kTableRadius]
+                                                    : (float)exp(-((dx * dx + dy * dy) / (2.0f * sigmaD * sigmaD)));
                             const float gr = exp(-(dist * dist) / (2.0 * sigmaR * sigmaR));
                             const float weight = gd * gr;
                             sum_weight += weight;
@@ -60,7 +81,7 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict_
                     }
             if (sum_weight > 0.0f) result = sum / sum_weight;
         }
-        out[(size_t)blockIdx.z * width * height + y * width + x] = result;
+        out[(size_t)bz * width * height + y * width + x] = result;
     }
     if (holes) {
         const unsigned m = __ballot_sync(0xffffffffu, hole);
@@ -68,32 +89,38 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) bilateral_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
+                                                        int height, float sigmaD, float sigmaR, int32_t *holes) {
+    __shared__ float s_table[kTableDiameter * kTableDiameter];
+    spatial_table_fill(s_table, sigmaD, (int)ceil(2.0 * sigmaD));
+    __syncthreads();
+    bilateral_tile(in, out, width, height, sigmaD, sigmaR, holes, blockIdx.x, blockIdx.y, blockIdx.z, s_table);
+}
+
 // median_fill_depthmap_kernel (dkernel.cu:89-140).  Valid pixels are copied.  A hole takes the order statistic the
 // reference reads out of its sorted 11x11 window: the ((n+1)/2)-th smallest (0-based) of the n valid values, each
 // quantised to millimetres as (int)(1000 d + 0.5f).  (For n < 2 the reference indexes past its array; here: 0.)
 // The reference bubble-sorts 121 values per hole in one thread; here a warp (32 pixels of a row) handles its holes one
-// after the other TOGETHER: the lanes load the window into shared memory (4 values each), every lane ranks its own four
-// candidates against all 121 (broadcast reads), and the lane whose candidate has the wanted rank publishes it -- a chain
-// of ~500 steps per hole instead of ~15 000 in the thread that owns it.
-// `gate` (may be NULL): the pass does nothing when *gate == 0.  `holes_out` (may be NULL): counts the zeros written.
-__global__ void __launch_bounds__(256) median_fill_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
-                                                          int height, const int32_t *gate, int32_t *holes_out) {
-    if (gate && *gate == 0) return;
-    __shared__ int s_win[8][128];
+// after the other TOGETHER: the lanes hold the window (4 values each) and find the wanted order statistic by a radix
+// select over the bits the window's values differ in -- per bit four votes and a count; a window whose depths span less
+// than a metre resolves in ten rounds, ~200 warp instructions per hole instead of ~15 000 steps in the thread that owns
+// it.
+__device__ __forceinline__ void median_fill_tile(const float *__restrict__ in, float *__restrict__ out, int width, int height,
+                                                 int32_t *holes_out, int bx, int by, int bz) {
     const unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + warp;
-    const float *img = in + (size_t)blockIdx.z * width * height;
+    const int x = bx * 32 + lane, y = by * 8 + warp;
+    const float *img = in + (size_t)bz * width * height;
     const bool inside = x < width && y < height;
     const float cur = inside ? img[y * width + x] : 1.0f;
     float result = cur;
-    int *win = s_win[warp];
     unsigned todo = __ballot_sync(kFull, inside && !depth_valid(cur));
     while (todo) {
         const int h = __ffs(todo) - 1;  // the hole lane served now: pixel (hx, y)
         todo &= todo - 1;
-        const int hx = blockIdx.x * 32 + h;
-        int mine[4];
+        const int hx = bx * 32 + h;
+        unsigned key[4];  // quantised depth, sign bit flipped: unsigned order == the reference's int order
+        bool alive[4];
         int n = 0;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
@@ -106,45 +133,58 @@ __global__ void __launch_bounds__(256) median_fill_kernel(const float *__restric
                     if (depth_valid(d)) q = (int)(1000 * d + 0.5f);
                 }
             }
-            mine[r] = q;
-            win[e] = q;
             // (a valid depth can quantise to a non-positive value only if it is below 0.5 mm or negative; such entries stay
             // in the ranking, exactly as in the reference's array)
-            n += __popc(__ballot_sync(kFull, e < kFillCells && q != -1 ? true : false));
+            alive[r] = q != -1;
+            key[r] = (unsigned)q ^ 0x80000000u;
+            n += __popc(__ballot_sync(kFull, alive[r]));
         }
-        __syncwarp();
         int val = 0;
         if (n >= 2) {
-            const int k = (n + 1) / 2;  // rank among the valid values, ascending
-            int found = 0, fv = 0;
+            int k = (n + 1) / 2;  // rank among the valid values, ascending
+            // bits on which all valid values agree need no vote
+            unsigned mine = 0;
+            bool have = false;
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int v = mine[r];
-                int less = 0, equal = 0;
-                if (v != -1) {
-                    for (int j = 0; j < kFillCells; j++) {
-                        const int w = win[j];
-                        less += (w != -1) & (w < v);
-                        equal += w == v;
-                    }
-                    if (less <= k && k < less + equal) { found = 1; fv = v; }
-                }
+            for (int r = 3; r >= 0; r--)
+                if (alive[r]) { mine = key[r]; have = true; }
+            const unsigned who = __ballot_sync(kFull, have);
+            const unsigned ref = __shfl_sync(kFull, mine, __ffs(who) - 1);
+            unsigned diff = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) diff |= alive[r] ? key[r] ^ ref : 0u;
+            diff = __reduce_or_sync(kFull, diff);
+            const int top = 32 - __clz(diff);  // bits [0, top) differ somewhere
+            unsigned prefix = top >= 32 ? 0u : ref & ~((1u << top) - 1u);
+            for (int bit = top - 1; bit >= 0; bit--) {
+                int zeros = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) zeros += __popc(__ballot_sync(kFull, alive[r] && !((key[r] >> bit) & 1u)));
+                const bool one = k >= zeros;  // the wanted value has this bit set
+                if (one) { k -= zeros; prefix |= 1u << bit; }
+#pragma unroll
+                for (int r = 0; r < 4; r++) alive[r] = alive[r] && (((key[r] >> bit) & 1u) != 0u) == one;
             }
-            const unsigned who = __ballot_sync(kFull, found);
-            val = __shfl_sync(kFull, fv, who ? __ffs(who) - 1 : 0);  // every lane that found it holds the same value
+            val = (int)(prefix ^ 0x80000000u);
         }
         if (lane == h) result = val <= 0 ? 0.0f : 0.001f * (float)val;
-        __syncwarp();
     }
     bool hole = false;
     if (inside) {
-        out[(size_t)blockIdx.z * width * height + y * width + x] = result;
+        out[(size_t)bz * width * height + y * width + x] = result;
         hole = result == 0.0f;
     }
     if (holes_out) {
         const unsigned m = __ballot_sync(kFull, hole);
         if (lane == 0 && m) atomicAdd(holes_out, __popc(m));
     }
+}
+
+// `gate` (may be NULL): the pass does nothing when *gate == 0.  `holes_out` (may be NULL): counts the zeros written.
+__global__ void __launch_bounds__(256) median_fill_kernel(const float *__restrict__ in, float *__restrict__ out, int width,
+                                                          int height, const int32_t *gate, int32_t *holes_out) {
+    if (gate && *gate == 0) return;
+    median_fill_tile(in, out, width, height, holes_out, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 __device__ __forceinline__ float3 normal_from_points(float3 cc, float3 pc, float3 cp, float3 mc, float3 cm) {
@@ -174,12 +214,11 @@ __device__ __forceinline__ float3 camera_point(const float *img, const float4 k,
 
 // convert_depth_to_cameraspace_kernel (dkernel.cu:142-170) + compute_normals_kernel (:172-211) in one pass: the four
 // neighbours' camera-space points are recomputed from the depth image instead of read back from the camspace image.
-__global__ void __launch_bounds__(256) camspace_normals_kernel(const float *__restrict__ depth, const float *__restrict__ intr,
-                                                               float *__restrict__ camspace, float *__restrict__ normals,
-                                                               int width, int height) {
-    const unsigned x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+__device__ __forceinline__ void camspace_normals_tile(const float *__restrict__ depth, const float *__restrict__ intr,
+                                                      float *__restrict__ camspace, float *__restrict__ normals, int width,
+                                                      int height, int bx, int by, int b) {
+    const unsigned x = bx * 32 + (threadIdx.x & 31), y = by * 8 + (threadIdx.x >> 5);
     if (x >= (unsigned)width || y >= (unsigned)height) return;
-    const int b = blockIdx.z;
     const float *img = depth + (size_t)b * width * height;
     const float4 k = *reinterpret_cast<const float4 *>(intr + (size_t)b * 4);  // fx, fy, mx, my
     const size_t o = ((size_t)b * height * width + (size_t)y * width + x) * 3;
@@ -193,6 +232,39 @@ __global__ void __launch_bounds__(256) camspace_normals_kernel(const float *__re
         out = normal_from_points(cc, pc, cp, mc, cm);
     }
     normals[o] = out.x; normals[o + 1] = out.y; normals[o + 2] = out.z;
+}
+
+__global__ void __launch_bounds__(256) camspace_normals_kernel(const float *__restrict__ depth, const float *__restrict__ intr,
+                                                               float *__restrict__ camspace, float *__restrict__ normals,
+                                                               int width, int height) {
+    camspace_normals_tile(depth, intr, camspace, normals, width, height, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// The fill rounds and the normals of Depth2Normals.forward (depth_utils.py:86-95) as one grid-resident launch: passes over
+// 32x8-pixel tiles dealt round-robin to the CTAs, a grid barrier where a pass reads what the previous one wrote, and a
+// loop that ends when a round leaves no hole.  (The bilateral filter in front stays a launch of its own: it is bound by
+// double-precision throughput and wants every tile in flight at its own, higher occupancy.)
+__global__ void __launch_bounds__(256) fill_rounds_normals_kernel(float *depth, const float *__restrict__ intr, float *filtered,
+                                                                  float *camspace, float *normals, int32_t *hole_counts,
+                                                                  int width, int height, int batch, int rounds) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int gx = (width + 31) / 32, gy = (height + 7) / 8, tiles = gx * gy * batch;
+    auto for_tiles = [&](auto &&body) {
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int bz = t / (gx * gy), r = t - bz * gx * gy;
+            body(r % gx, r / gx, bz);
+        }
+    };
+    for (int r = 0; r < rounds; r++) {
+        // hole_counts[r] is final: its adds happened before the previous barrier (or in the bilateral launch)
+        if (*reinterpret_cast<volatile int32_t *>(hole_counts + r) == 0) break;
+        for_tiles([&](int bx, int by, int bz) { median_fill_tile(filtered, depth, width, height, hole_counts + r + 1, bx, by, bz); });
+        grid.sync();
+        for_tiles([&](int bx, int by, int bz) { median_fill_tile(depth, filtered, width, height, nullptr, bx, by, bz); });
+        grid.sync();
+    }
+    for_tiles([&](int bx, int by, int bz) { camspace_normals_tile(depth, intr, camspace, normals, width, height, bx, by, bz); });
 }
 
 // compute_normals_kernel (dkernel.cu:172-211) on a camera-space image given by the caller
@@ -273,6 +345,24 @@ int spsg_depth_to_normals(float *depth, const float *intrinsics, float *filtered
     SPSG_CUDA_TRY(cudaMemsetAsync(hole_counts, 0, sizeof(int32_t) * (SPSG_DEPTH_MAX_FILL_ROUNDS + 1), st));
     bilateral_kernel<<<grid, 256, 0, st>>>(depth, filtered, width, height, sigma_d, sigma_r, hole_counts);  // depth_utils.py:85
     SPSG_CUDA_TRY(cudaGetLastError());
+    {
+        // fill rounds + normals: one cooperative launch when the device has them, with as many CTAs as are resident at
+        // once or, if the tiles need several turns, the count that gives every CTA the same number of turns
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        SPSG_CUDA_TRY(cudaGetDevice(&dev));
+        SPSG_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        SPSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SPSG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_rounds_normals_kernel, 256, 0));
+        if (coop && per_sm > 0 && !getenv("SPSG_DEPTH_NO_COOPERATIVE")) {
+            const long long tiles = (long long)grid.x * grid.y * grid.z, room = (long long)sms * per_sm;
+            const long long turns = (tiles + room - 1) / room;
+            const int ctas = (int)((tiles + turns - 1) / turns);
+            void *args[] = {&depth, &intrinsics, &filtered, &camspace, &normals, &hole_counts, &width, &height, &batch,
+                            const_cast<int *>(&rounds)};
+            SPSG_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)fill_rounds_normals_kernel, dim3(ctas), dim3(256), args, 0, st));
+            return SPSG_OK;
+        }
+    }
     for (int r = 0; r < rounds; r++) {
         // one call of median_fill_depthmap(filt, depth, 2) (depth_utils.py:55-59,90): depth <- fill(filtered), filtered <- fill(depth);
         // both passes return immediately once the previous round left no hole

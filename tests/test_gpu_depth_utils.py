@@ -111,3 +111,31 @@ def test_depth2normals_returns_none_when_holes_remain(cuda_device):
     assert mod(d_mine, intr) is None
     assert int((d_mine == 0).sum()) > 0              # partially filled in place, holes remain
     assert int((d_mine == 0).sum()) < int((depth == 0).sum())
+
+
+@pytest.mark.parametrize("shape", [(3, 96, 128), (8, 256, 320), (2, 61, 75)])
+def test_single_launch_pipeline_equals_launch_per_pass(cuda_device, shape, monkeypatch):
+    """The fill rounds + normals of Depth2Normals are one cooperative launch (grid barriers between the passes);
+    SPSG_DEPTH_NO_COOPERATIVE selects the
+    launch-per-pass form of the same passes.  Same normals, filled depth, helper images and hole counts, bit for bit --
+    including frames with more tiles than resident CTAs, ragged tile edges and a hole no round can close."""
+    from spsg_b200.depth_utils import Depth2Normals
+    b, h, w = shape
+    depth, intr = _frames(cuda_device, batch=b, h=h, w=w, holes=0.04, hole_blocks=True, seed=9)
+    depth[0, :, 5:50, 8:60] = 0.0                    # frame 0 keeps holes for a few rounds
+    results = []
+    for no_coop in (False, True):
+        if no_coop:
+            monkeypatch.setenv("SPSG_DEPTH_NO_COOPERATIVE", "1")
+        else:
+            monkeypatch.delenv("SPSG_DEPTH_NO_COOPERATIVE", raising=False)
+        d = depth.clone()
+        mod = Depth2Normals(b, w, h, 5.0, 300.0, device=cuda_device)
+        out = mod(d, intr)
+        torch.cuda.synchronize()
+        results.append((out, d, mod.filter_helper.clone(), mod.camspace.clone(), mod.normals.clone(), mod.hole_counts.clone()))
+    one, many = results
+    assert (one[0] is None) == (many[0] is None)
+    for x, y, name in zip(one[1:], many[1:], ("depth", "filtered", "camspace", "normals", "hole counts")):
+        assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                           y.view(torch.int32) if y.dtype == torch.float32 else y), name
