@@ -379,7 +379,7 @@ class Ours:
             main.wait_event(copied[slot])
             d = slot_views(slots[slot], packed[k][1])
             sdf, col, sem = (t.detach().requires_grad_(True) for t in heads[k])
-            locs, v_sdf, v_col, v_sem = SP.sparsify_predictions(sdf, S.TRUNCATION, None, col, sem)
+            locs, v_sdf, v_col, v_sem = SP.sparsify_predictions(sdf, S.TRUNCATION, None, col, sem, raycaster=mods[k])
             nrm = NRM.compute_normals_sparse(locs, v_sdf, S.DIMS_ZYX, transform=torch.inverse(d["view"][::F]), num_chunks=B)
             total, _, _ = render(mods[k], locs, v_sdf, v_col, nrm, v_sem, d["view"], d["intr"], images_depth=d["t_depth"],
                                  images_color=d["t_color"], target2d_label=d["t_label"], weight_semantic_class=cw,

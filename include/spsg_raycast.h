@@ -56,6 +56,9 @@ enum {
     SPSG_FLAG_GRADS_CLEARED = 1u << 3, /* backward only: rows [0,N) of d_* were cleared by the matching forward */
     SPSG_FLAG_SMEM_MAPS = 1u << 5,     /* debug: march maps staged in shared memory (TMA) even for several chunks          */
     SPSG_FLAG_GLOBAL_MAPS = 1u << 6,   /* debug: march maps read through L1 + one global tile counter even for one chunk   */
+    SPSG_FLAG_INDEX_PREBUILT = 1u << 7, /* forward: sparse_mapping and the workspace's dense SDF brick already hold exactly
+                                          these locs / vals_sdf (written by spsg_sparsify_locs_indexed): skip the -1 / NaN
+                                          fill and the index pass (only mapping3dto2d_num is reset)                          */
     SPSG_FLAG_DETERMINISTIC_GRADS = 1u << 4 /* backward, several views per chunk: add a voxel's per-view means in view order
                                                without float atomics (bit-reproducible; the gather takes ~30 % longer) */
 };
@@ -280,6 +283,16 @@ SPSG_API int spsg_sparsify_count(const float *sdf, const uint8_t *empty, int64_t
 SPSG_API int spsg_sparsify_locs(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz, int32_t dimy,
                                 int32_t dimx, float truncation, const void *scratch, int64_t *locs, int64_t num_locs,
                                 void *stream);
+/* Step 2 feeding the raycaster directly: as spsg_sparsify_locs, and in the same pass, for EVERY
+ * cell of the grid, what construct_dense_sparse_mapping (raycast_rgbd_cuda_kernel.cu:346-362, 506-533) and this
+ * implementation's dense-brick pass would derive from those rows afterwards: sparse_mapping[cell] = row of the cell or -1,
+ * and the dense SDF brick at the start of `raycast_workspace` (its first B*Dz*Dy*Dx floats; the workspace of the forward
+ * that will render these rows, at least spsg_raycast_workspace_bytes() of that call) = the cell's SDF or "absent".  A
+ * forward over exactly these rows, with vals_sdf = the gathered head values, may then be called with
+ * SPSG_FLAG_INDEX_PREBUILT.  sparse_mapping: (B,Dz,Dy,Dx) int32; it and the workspace 16-byte aligned; num_locs < 2^31. */
+SPSG_API int spsg_sparsify_locs_indexed(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz,
+                                        int32_t dimy, int32_t dimx, float truncation, const void *scratch, int64_t *locs,
+                                        int64_t num_locs, int32_t *sparse_mapping, void *raycast_workspace, void *stream);
 SPSG_API int spsg_dense_gather(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,
                                int32_t num_chunks, int32_t dimz, int32_t dimy, int32_t dimx, void *stream);
 SPSG_API int spsg_dense_scatter(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,

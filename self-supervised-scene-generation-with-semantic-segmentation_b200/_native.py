@@ -17,6 +17,7 @@ SPSG_FLAG_GRADS_CLEARED = 1 << 3
 SPSG_FLAG_DETERMINISTIC_GRADS = 1 << 4
 SPSG_FLAG_SMEM_MAPS = 1 << 5
 SPSG_FLAG_GLOBAL_MAPS = 1 << 6
+SPSG_FLAG_INDEX_PREBUILT = 1 << 7
 SPSG_LOSS_OUT_FLOATS = 8
 SPSG_DEPTH_MAX_FILL_ROUNDS = 64
 
@@ -28,7 +29,8 @@ EXPORTS = (
     "spsg_normals_backward", "spsg_losses2d_forward", "spsg_losses2d_backward",
     "spsg_depth_bilateral_filter", "spsg_depth_median_fill", "spsg_depth_to_cameraspace", "spsg_depth_to_normals",
     "spsg_depth_compute_normals",
-    "spsg_sparsify_scratch_bytes", "spsg_sparsify_count", "spsg_sparsify_locs", "spsg_dense_gather", "spsg_dense_scatter",
+    "spsg_sparsify_scratch_bytes", "spsg_sparsify_count", "spsg_sparsify_locs", "spsg_sparsify_locs_indexed",
+    "spsg_dense_gather", "spsg_dense_scatter",
     "spsg_labels_from_render",
 )
 
@@ -125,6 +127,8 @@ def _load():
     lib.spsg_sparsify_count.argtypes = [vp, vp, i64, f32, vp, sz, vp, vp]
     lib.spsg_sparsify_locs.restype = ctypes.c_int
     lib.spsg_sparsify_locs.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, i64, vp]
+    lib.spsg_sparsify_locs_indexed.restype = ctypes.c_int
+    lib.spsg_sparsify_locs_indexed.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, i64, vp, vp, vp]
     lib.spsg_dense_gather.restype = ctypes.c_int
     lib.spsg_dense_gather.argtypes = [dp, i32, vp, i64, i32, i32, i32, i32, vp]
     lib.spsg_dense_scatter.restype = ctypes.c_int

@@ -119,6 +119,7 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     double *accum = (double *)(ws + L.loss_off);
     const size_t cells = (size_t)p->num_chunks * p->dimz * p->dimy * p->dimx;
     const int sms = sm_count();
+    const bool prebuilt = (p->flags & SPSG_FLAG_INDEX_PREBUILT) && p->num_locs > 0;
 
     {
         // sparse_mapping := -1 (kernel.cu:515), dense brick := NaN (0xffffffff: every voxel absent), block marks / list
@@ -127,16 +128,22 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         memset(&f, 0, sizeof(f));
         f.ptr[0] = build_index ? (uint32_t *)sparse_mapping : nullptr; f.words[0] = cells; f.value[0] = 0xffffffffu;
         f.ptr[1] = (uint32_t *)dense; f.words[1] = L.dense_bytes / 4; f.value[1] = 0xffffffffu;
+        if (prebuilt) {
+            // index and brick were written together with locs (spsg_sparsify_locs_indexed): what is left of the two
+            // passes is the reset of the voxel -> pixel counters, rows [0, F * N)
+            f.ptr[0] = (uint32_t *)mapping3dto2d_num; f.words[0] = (size_t)p->views_per_chunk * p->num_locs; f.value[0] = 0u;
+            f.ptr[1] = nullptr; f.words[1] = 0;
+        }
         f.ptr[2] = (uint32_t *)(ws + L.zero_off); f.words[2] = L.zero_bytes / 4; f.value[2] = 0u;
         if (clear_grads && p->num_locs > 0 &&
             (!clear_grads->d_color || !clear_grads->d_depth || !clear_grads->d_normal || !clear_grads->d_semantic))
             return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL gradient pointer in clear_grads");
-        const size_t vecs = (cells * (build_index ? 2 : 1) + L.zero_bytes / 4) / 4;
+        const size_t vecs = ((prebuilt ? f.words[0] : cells * (build_index ? 2 : 1)) + L.zero_bytes / 4) / 4;
         const unsigned blocks = (unsigned)std::min<size_t>((vecs + 1023) / 1024 + 1, (size_t)sms * 8);
         fill_kernel<<<blocks, 256, 0, st>>>(f);
         CUDA_TRY(cudaGetLastError());
     }
-    if (p->num_locs > 0) {
+    if (p->num_locs > 0 && !prebuilt) {
         const unsigned blocks = (unsigned)((p->num_locs + 255) / 256);
         if (build_index)
             index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,

@@ -39,14 +39,16 @@ Scratch carve(void *scratch, long long tiles) {
     return s;
 }
 
-// bit k of the result: cell (first + k) passes |sdf| < truncation (NaN fails, like torch) and is not marked empty
-__device__ __forceinline__ unsigned thread_mask(const float *__restrict__ sdf, const uint8_t *__restrict__ empty,
-                                                long long first, long long cells, float truncation) {
+// bit k of the result: cell (first + k) passes |sdf| < truncation (NaN fails, like torch) and is not marked empty;
+// v[k] = the cell's SDF value (NaN beyond the end of the grid)
+__device__ __forceinline__ unsigned thread_cells(const float *__restrict__ sdf, const uint8_t *__restrict__ empty,
+                                                 long long first, long long cells, float truncation,
+                                                 float (&v)[kCellsPerThread]) {
     unsigned m = 0u;
     if (first + kCellsPerThread <= cells) {  // (sdf is 16-byte aligned and first is a multiple of 8)
         const float4 a = __ldg(reinterpret_cast<const float4 *>(sdf + first));
         const float4 b = __ldg(reinterpret_cast<const float4 *>(sdf + first) + 1);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
         for (int k = 0; k < 8; k++) m |= (fabsf(v[k]) < truncation ? 1u : 0u) << k;
         if (empty && m) {
@@ -58,10 +60,22 @@ __device__ __forceinline__ unsigned thread_mask(const float *__restrict__ sdf, c
             }
         }
     } else {
-        for (int k = 0; k < kCellsPerThread && first + k < cells; k++)
-            if (fabsf(__ldg(sdf + first + k)) < truncation && !(empty && empty[first + k])) m |= 1u << k;
+#pragma unroll
+        for (int k = 0; k < kCellsPerThread; k++) {
+            v[k] = __int_as_float(0x7fffffff);
+            if (first + k < cells) {
+                v[k] = __ldg(sdf + first + k);
+                if (fabsf(v[k]) < truncation && !(empty && empty[first + k])) m |= 1u << k;
+            }
+        }
     }
     return m;
+}
+
+__device__ __forceinline__ unsigned thread_mask(const float *__restrict__ sdf, const uint8_t *__restrict__ empty,
+                                                long long first, long long cells, float truncation) {
+    float v[kCellsPerThread];
+    return thread_cells(sdf, empty, first, cells, truncation, v);
 }
 
 __global__ void __launch_bounds__(kTileThreads) sparsify_count_kernel(const float *__restrict__ sdf,
@@ -123,15 +137,22 @@ __global__ void __launch_bounds__(1024) sparsify_scan_kernel(const int32_t *__re
     }
 }
 
+// kIndexed: the same pass also writes, for EVERY cell, what the raycaster's fill + index passes derive from `locs`
+// (kernel.cu:346-362, 515 and the dense SDF brick of this implementation): index[cell] = row of the cell or -1,
+// brick[cell] = its SDF or NaN (absent) -- two coalesced 32-byte stores per thread instead of a 32-byte read and two
+// scattered 4-byte writes per row in a later launch.
+template <bool kIndexed>
 __global__ void __launch_bounds__(kTileThreads) sparsify_write_kernel(const float *__restrict__ sdf,
                                                                       const uint8_t *__restrict__ empty, long long cells,
                                                                       int dimz, int dimy, int dimx, float truncation,
                                                                       const long long *__restrict__ offsets,
-                                                                      longlong4 *__restrict__ locs, long long num_locs) {
+                                                                      longlong4 *__restrict__ locs, long long num_locs,
+                                                                      int32_t *__restrict__ index, float *__restrict__ brick) {
     __shared__ int s_warp[kTileThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long first = ((long long)blockIdx.x * kTileThreads + threadIdx.x) * kCellsPerThread;
-    const unsigned m = first < cells ? thread_mask(sdf, empty, first, cells, truncation) : 0u;
+    float v[kCellsPerThread];
+    const unsigned m = first < cells ? thread_cells(sdf, empty, first, cells, truncation, v) : 0u;
     const int n = __popc(m);
     int inc = n;
 #pragma unroll
@@ -143,7 +164,8 @@ __global__ void __launch_bounds__(kTileThreads) sparsify_write_kernel(const floa
     __syncthreads();
     int before = inc - n;
     for (int w = 0; w < warp; w++) before += s_warp[w];
-    if (!m) return;
+    if (!kIndexed && !m) return;
+    if (first >= cells) return;
     long long pos = offsets[blockIdx.x] + before;
     // (b, z, y, x) of the thread's first cell, then x runs with carries
     const long long plane = (long long)dimy * dimx;
@@ -151,10 +173,15 @@ __global__ void __launch_bounds__(kTileThreads) sparsify_write_kernel(const floa
     const long long bz = rest / plane;
     rest -= bz * plane;
     long long b = bz / dimz, z = bz - b * dimz, y = rest / dimx, x = rest - y * dimx;
+    int row[kCellsPerThread];
 #pragma unroll
     for (int k = 0; k < kCellsPerThread; k++) {
+        row[k] = -1;
         if ((m >> k) & 1u) {
-            if (pos < num_locs) locs[pos] = make_longlong4(z, y, x, b);  // train.py:498 column order
+            if (pos < num_locs) {
+                locs[pos] = make_longlong4(z, y, x, b);  // train.py:498 column order
+                row[k] = (int)pos;
+            }
             pos++;
         }
         if (++x == dimx) {
@@ -163,6 +190,26 @@ __global__ void __launch_bounds__(kTileThreads) sparsify_write_kernel(const floa
                 y = 0;
                 if (++z == dimz) { z = 0; b++; }
             }
+        }
+    }
+    if (kIndexed) {
+        const float absent = __int_as_float(0xffffffff);  // the brick's "no voxel here" (what the forward's fill writes)
+        if (first + kCellsPerThread <= cells) {  // (index and brick are 16-byte aligned, first is a multiple of 8)
+            int4 *ip = reinterpret_cast<int4 *>(index + first);
+            float4 *bp = reinterpret_cast<float4 *>(brick + first);
+            ip[0] = make_int4(row[0], row[1], row[2], row[3]);
+            ip[1] = make_int4(row[4], row[5], row[6], row[7]);
+            bp[0] = make_float4(row[0] < 0 ? absent : v[0], row[1] < 0 ? absent : v[1], row[2] < 0 ? absent : v[2],
+                                row[3] < 0 ? absent : v[3]);
+            bp[1] = make_float4(row[4] < 0 ? absent : v[4], row[5] < 0 ? absent : v[5], row[6] < 0 ? absent : v[6],
+                                row[7] < 0 ? absent : v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kCellsPerThread; k++)
+                if (first + k < cells) {
+                    index[first + k] = row[k];
+                    brick[first + k] = row[k] < 0 ? absent : v[k];
+                }
         }
     }
 }
@@ -283,22 +330,48 @@ SPSG_API int spsg_sparsify_count(const float *sdf, const uint8_t *empty, int64_t
     return SPSG_OK;
 }
 
-SPSG_API int spsg_sparsify_locs(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz, int32_t dimy,
-                                int32_t dimx, float truncation, const void *scratch, int64_t *locs, int64_t num_locs,
-                                void *stream) {
+static int sparsify_locs_impl(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz, int32_t dimy,
+                              int32_t dimx, float truncation, const void *scratch, int64_t *locs, int64_t num_locs,
+                              int32_t *index, float *brick, bool indexed, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = check_grid(num_chunks, dimz, dimy, dimx)) return rc;
     if (!sdf || !scratch) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "NULL sdf / scratch");
     if (num_locs < 0 || (num_locs > 0 && !locs)) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "bad locs");
     if (reinterpret_cast<uintptr_t>(locs) & 15u) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "locs must be 16-byte aligned");
-    if (num_locs == 0) return SPSG_OK;
+    if (indexed) {
+        if (!index || !brick) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "NULL index / brick");
+        if ((reinterpret_cast<uintptr_t>(index) & 15u) || (reinterpret_cast<uintptr_t>(brick) & 15u))
+            return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "index and brick must be 16-byte aligned");
+        if (num_locs >= (1ll << 31)) return spsg_internal_fail(SPSG_ERR_INVALID_ARGUMENT, "num_locs exceeds 32-bit indexing");
+    } else if (num_locs == 0) {
+        return SPSG_OK;
+    }
     const long long cells = (long long)num_chunks * dimz * dimy * dimx;
     const long long tiles = num_tiles(cells);
     const Scratch s = carve(const_cast<void *>(scratch), tiles);
-    sparsify_write_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(sdf, empty, cells, dimz, dimy, dimx, truncation, s.offsets,
-                                                                    reinterpret_cast<longlong4 *>(locs), num_locs);
+    if (indexed)
+        sparsify_write_kernel<true><<<(unsigned)tiles, kTileThreads, 0, st>>>(sdf, empty, cells, dimz, dimy, dimx, truncation, s.offsets,
+                                                                              reinterpret_cast<longlong4 *>(locs), num_locs, index, brick);
+    else
+        sparsify_write_kernel<false><<<(unsigned)tiles, kTileThreads, 0, st>>>(sdf, empty, cells, dimz, dimy, dimx, truncation, s.offsets,
+                                                                               reinterpret_cast<longlong4 *>(locs), num_locs, nullptr, nullptr);
     SPSG_CUDA_TRY(cudaGetLastError());
     return SPSG_OK;
+}
+
+SPSG_API int spsg_sparsify_locs(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz, int32_t dimy,
+                                int32_t dimx, float truncation, const void *scratch, int64_t *locs, int64_t num_locs,
+                                void *stream) {
+    return sparsify_locs_impl(sdf, empty, num_chunks, dimz, dimy, dimx, truncation, scratch, locs, num_locs, nullptr, nullptr,
+                              false, stream);
+}
+
+SPSG_API int spsg_sparsify_locs_indexed(const float *sdf, const uint8_t *empty, int32_t num_chunks, int32_t dimz,
+                                        int32_t dimy, int32_t dimx, float truncation, const void *scratch, int64_t *locs,
+                                        int64_t num_locs, int32_t *sparse_mapping, void *raycast_workspace, void *stream) {
+    // the dense SDF brick is the first num_chunks * Dz * Dy * Dx floats of the raycast workspace (Layout::dense_off == 0)
+    return sparsify_locs_impl(sdf, empty, num_chunks, dimz, dimy, dimx, truncation, scratch, locs, num_locs, sparse_mapping,
+                              static_cast<float *>(raycast_workspace), true, stream);
 }
 
 SPSG_API int spsg_dense_gather(const spsg_dense_payload *payloads, int32_t count, const int64_t *locs, int64_t num_locs,

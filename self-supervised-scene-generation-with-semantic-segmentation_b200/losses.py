@@ -93,7 +93,10 @@ def fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, v
     gb = N.grad_buffers(m.d_color, m.d_depth, m.d_normal, m.d_semantic) if clear_grads else None
     owner = _module_workspace(m)
     with rc.device_guard(dev):
-        ws = owner.get(dev, N.workspace_bytes(p))
+        nbytes = N.workspace_bytes(p)
+        prebuilt = owner.take_prebuilt(locs, nbytes)  # index + brick written with locs by sparsify_predictions(raycaster=m)
+        ws = owner.get(dev, nbytes)
+        p.flags |= prebuilt
         N.check(N.lib.spsg_raycast_forward_loss(
             ctypes.byref(p), N.ptr(m.sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_colors),
             N.ptr(vals_normals), N.ptr(vals_semantic), N.ptr(view_matrix), N.ptr(intrinsic_params),
@@ -101,6 +104,9 @@ def fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, v
             N.ptr(m.mapping3dto2d), N.ptr(m.mapping3dto2d_num), ctypes.byref(tg), N.ptr(loss_out),
             ctypes.byref(gb) if gb is not None else None, N.ptr(ws), ws.numel(), rc._stream(dev)))
         owner.filled(p)
+        if prebuilt:
+            owner.mark_prebuilt(locs)
+            p.flags &= ~N.SPSG_FLAG_INDEX_PREBUILT  # (the params go on to the backward)
     return p, tg, loss_out
 
 

@@ -15,6 +15,8 @@ Same four entry points, positional tensors, in-place outputs and error behaviour
 import ctypes
 from collections import OrderedDict
 
+import weakref
+
 import torch
 
 from . import _native as N
@@ -99,13 +101,28 @@ class ModuleWorkspace:
     """The workspace of one raycaster module: an explicit buffer it owns, stamped by every forward."""
 
     def __init__(self):
-        self.ws, self.stamp = None, None
+        self.ws, self.stamp, self._prebuilt = None, None, None
 
     def get(self, device, nbytes):
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
             self.ws = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-            self.stamp = None
+            self.stamp, self._prebuilt = None, None
         return self.ws
+
+    # The voxel index and the dense SDF brick can be written together with ``locs`` (sparsify.sparsify_predictions(...,
+    # raycaster=m)); the forward that renders exactly that ``locs`` tensor then skips its fill and index passes.  Any other
+    # forward on the module overwrites them, which drops the mark.
+    def mark_prebuilt(self, locs):
+        self._prebuilt = (weakref.ref(locs), locs._version, locs.shape[0])
+
+    def take_prebuilt(self, locs, nbytes):
+        """SPSG_FLAG_INDEX_PREBUILT if index + brick in this workspace belong to ``locs`` (same tensor object, unmodified), else
+        0; either way the mark is re-derived by the caller after the forward."""
+        mark, self._prebuilt = self._prebuilt, None
+        if mark is None or self.ws is None or self.ws.numel() < nbytes:
+            return 0
+        ref, version, n = mark
+        return N.SPSG_FLAG_INDEX_PREBUILT if ref() is locs and locs._version == version and locs.shape[0] == n else 0
 
     def filled(self, p):
         self.stamp = _stamp(p)
@@ -195,7 +212,9 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
     with device_guard(dev):
         nbytes = N.workspace_bytes(p)
         if workspace_owner is not None:
+            prebuilt = workspace_owner.take_prebuilt(locs, nbytes) if build_index else 0
             ws = workspace_owner.get(dev, nbytes)
+            p.flags |= prebuilt
         else:
             ws = workspace(dev, nbytes, sparse_mapping, stamp=_stamp(p))
         args = (ctypes.byref(p), N.ptr(sparse_mapping), N.ptr(locs), N.ptr(vals_sdf), N.ptr(vals_color),
@@ -218,6 +237,8 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
             N.check(N.lib.spsg_raycast_forward(*args, N.ptr(ws), ws.numel(), _stream(dev)))
         if workspace_owner is not None:
             workspace_owner.filled(p)
+            if p.flags & N.SPSG_FLAG_INDEX_PREBUILT:
+                workspace_owner.mark_prebuilt(locs)  # index and brick are untouched: still valid for these rows
     return ws
 
 

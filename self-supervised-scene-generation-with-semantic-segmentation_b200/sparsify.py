@@ -21,21 +21,7 @@ from . import _native as N
 from . import raycast_rgbd_cuda as rc
 
 _MAX_PAYLOADS = 4
-_scratch = {}
-
-
-def _scratch_for(device, nbytes):
-    key = (device.type, device.index)
-    buf = _scratch.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
-        _scratch[key] = buf
-    return buf
-
-
-def sparse_locs(sdf, truncation, empty=None):
-    """``locs`` (N,4) int64 rows (z, y, x, b) of the voxels with ``|sdf| < truncation`` (and ``~empty``), in
-    ``torch.nonzero`` order.  sdf / empty: (B,Dz,Dy,Dx) or (B,1,Dz,Dy,Dx); empty is a bool mask or None."""
+def _prepare(sdf, empty):
     if sdf.dim() == 5:
         if sdf.shape[1] != 1:
             raise RuntimeError("sdf must have one channel")
@@ -57,22 +43,84 @@ def sparse_locs(sdf, truncation, empty=None):
         sdf = sdf.clone()  # the kernels read 16-byte vectors
     if empty is not None and empty.data_ptr() % 8:
         empty = empty.clone()
+    return sdf, empty
+
+
+class CountedLocs:
+    """Step 1 of the compaction done ahead of time (``count_locs``): ``n`` rows will come out; the per-tile offsets wait in
+    a scratch buffer of their own until ``sparse_locs(..., counted=this)`` writes the rows."""
+
+    def __init__(self, sdf, empty, truncation, scratch, n):
+        self.sdf, self.empty, self.truncation, self.scratch, self.n = sdf, empty, float(truncation), scratch, n
+        self.version = sdf._version
+
+
+def count_locs(sdf, truncation, empty=None):
+    """How many voxels ``sparse_locs`` will return (one host synchronisation, the one ``torch.nonzero`` has), keeping the
+    work done: pass the result as ``counted=`` to ``sparse_locs`` / ``sparsify_predictions`` later.  Lets a training step
+    decide early (train.py:524-529) and build the rows late -- after other renders on the same raycaster -- so that
+    ``raycaster=`` still feeds the prediction render directly."""
+    sdf, empty = _prepare(sdf, empty)
     dev = sdf.device
-    B, dz, dy, dx = sdf.shape
     cells = sdf.numel()
     if cells == 0:
+        return CountedLocs(sdf, empty, truncation, None, 0)
+    with rc.device_guard(dev):
+        scratch = torch.empty(max(int(N.lib.spsg_sparsify_scratch_bytes(cells)), 256), dtype=torch.uint8, device=dev)
+        total = torch.empty(1, dtype=torch.int64, device=dev)
+        N.check(N.lib.spsg_sparsify_count(N.ptr(sdf), N.ptr(empty), cells, float(truncation), N.ptr(scratch),
+                                          scratch.numel(), N.ptr(total), rc._stream(dev)))
+        n = int(total.item())  # the host needs N to size the outputs (torch.nonzero synchronises for the same reason)
+    return CountedLocs(sdf, empty, truncation, scratch, n)
+
+
+def sparse_locs(sdf, truncation, empty=None, raycaster=None, counted=None):
+    """``locs`` (N,4) int64 rows (z, y, x, b) of the voxels with ``|sdf| < truncation`` (and ``~empty``), in
+    ``torch.nonzero`` order.  sdf / empty: (B,Dz,Dy,Dx) or (B,1,Dz,Dy,Dx); empty is a bool mask or None.
+
+    ``raycaster`` (a ``RaycastRGBD`` over the same grid): the pass that writes ``locs`` also writes the raycaster's voxel
+    index (``sparse_mapping``) and dense SDF brick for these rows, so the forward that renders the returned tensor with
+    the SDF values gathered from ``sdf`` skips its own fill and index passes (nothing goes through int64 ``locs`` twice).
+    The caller's promise: the ``vals_sdf`` passed with these ``locs`` are ``gather_dense(locs, sdf)``.
+    ``counted``: the result of ``count_locs`` on the same (unmodified) tensors."""
+    if counted is None:
+        counted = count_locs(sdf, truncation, empty)
+    else:
+        s2, _ = _prepare(sdf, empty)
+        if (s2.shape != counted.sdf.shape or s2.data_ptr() != counted.sdf.data_ptr() or s2._version != counted.version or
+                float(truncation) != counted.truncation):
+            raise RuntimeError("counted= belongs to another sdf tensor / truncation (or the tensor was modified since)")
+    sdf, empty, n, scratch = counted.sdf, counted.empty, counted.n, counted.scratch
+    dev = sdf.device
+    B, dz, dy, dx = sdf.shape
+    if sdf.numel() == 0:
         return torch.zeros(0, 4, dtype=torch.int64, device=dev)
     with rc.device_guard(dev):
-        scratch = _scratch_for(dev, N.lib.spsg_sparsify_scratch_bytes(cells))
-        total = torch.empty(1, dtype=torch.int64, device=dev)
         stream = rc._stream(dev)
-        N.check(N.lib.spsg_sparsify_count(N.ptr(sdf), N.ptr(empty), cells, float(truncation), N.ptr(scratch),
-                                          scratch.numel(), N.ptr(total), stream))
-        n = int(total.item())  # the host needs N to size the outputs (torch.nonzero synchronises for the same reason)
         locs = torch.empty(n, 4, dtype=torch.int64, device=dev)
-        N.check(N.lib.spsg_sparsify_locs(N.ptr(sdf), N.ptr(empty), B, dz, dy, dx, float(truncation), N.ptr(scratch),
-                                         N.ptr(locs), n, stream))
+        if raycaster is not None and _feeds(raycaster, sdf, n):
+            m = raycaster
+            # the workspace of the forward to come, sized for the most views the module renders (the brick sits at its start)
+            p = N.make_params(m.width, m.height, m.depth_min, m.depth_max, m.thresh_sample_dist, m.ray_increment,
+                              m.dims3d[2], m.dims3d[1], m.dims3d[0], m.batch_size, m.max_num_frames,
+                              m.mapping3dto2d.shape[1], n, 0)
+            ws = m.workspace.get(dev, N.workspace_bytes(p))
+            N.check(N.lib.spsg_sparsify_locs_indexed(N.ptr(sdf), N.ptr(empty), B, dz, dy, dx, float(truncation),
+                                                     N.ptr(scratch), N.ptr(locs), n, N.ptr(m.sparse_mapping), N.ptr(ws),
+                                                     stream))
+            m.workspace.mark_prebuilt(locs)
+        else:
+            N.check(N.lib.spsg_sparsify_locs(N.ptr(sdf), N.ptr(empty), B, dz, dy, dx, float(truncation), N.ptr(scratch),
+                                             N.ptr(locs), n, stream))
     return locs
+
+
+def _feeds(m, sdf, n):
+    """can the index + brick of raycaster ``m`` be written for this head: same grid, same device, rows within its buffers"""
+    ws = getattr(m, "workspace", None)
+    return (ws is not None and n > 0 and tuple(sdf.shape) == (m.batch_size,) + tuple(m.dims3d) and
+            m.sparse_mapping.device == sdf.device and tuple(m.sparse_mapping.shape) == tuple(sdf.shape) and
+            n * m.max_num_frames <= m.mapping3dto2d.shape[0])
 
 
 def _payload_array(dense, sparse):
@@ -135,10 +183,11 @@ def gather_dense(locs, *dense):
     return out if len(dense) > 1 else out[0]
 
 
-def sparsify_predictions(output_sdf, truncation, empty=None, *heads):
+def sparsify_predictions(output_sdf, truncation, empty=None, *heads, raycaster=None, counted=None):
     """train.py:494-509 in one call: ``(locs, sdf_values, *head_values)`` for the dense SDF head (B,1,Dz,Dy,Dx) and any
-    further heads (colour, semantics, a one-hot target volume, ...)."""
-    locs = sparse_locs(output_sdf, truncation, empty)
+    further heads (colour, semantics, a one-hot target volume, ...).  ``raycaster`` / ``counted``: see ``sparse_locs`` --
+    the rows feed that raycaster's next forward directly."""
+    locs = sparse_locs(output_sdf, truncation, empty, raycaster=raycaster, counted=counted)
     vals = gather_dense(locs, output_sdf, *heads)
     if not heads:
         vals = (vals,)

@@ -97,19 +97,22 @@ class ViewGuidedTrainStep:
         loss_sdf = lu.compute_geo_loss(target_for_sdf, None, output_sdf, known, weight, self.logweight_sdf)
         loss = self.w["occ"] * loss_occ + self.w["sdf"] * loss_sdf
         # ---- dense heads -> sparse raycaster inputs (train.py:494-509)
-        locs, sdf_vals, color_vals, sem_vals = sparsify.sparsify_predictions(output_sdf, T, empty, output_color,
-                                                                             output_semantic)
-        n = locs.shape[0]
+        # (counted first, written after the other two renders of the step: the rows then feed the prediction render
+        # directly -- voxel index and SDF brick written with them, see sparsify.sparse_locs)
+        counted = sparsify.count_locs(output_sdf, T, empty)
+        n = counted.n
         self.last = dict(num_locs=n, loss_occ=loss_occ.detach(), loss_sdf=loss_sdf.detach())
         if 0 < n <= self.raycaster.get_max_num_locs_per_sample() * self.batch_size:          # train.py:524-529
             view_matrix, intrinsics = sample["view_matrix"], sample["images_intrinsic"]
             transform = torch.inverse(view_matrix)                                             # train.py:544
-            output_normals = normals.compute_normals_sparse(locs, sdf_vals, self.dims3d, transform=transform)
             if self.render_input:
                 self._render_input(inputs, view_matrix, intrinsics, transform)
             with torch.no_grad():
                 target2d_label = self._target_labels(target_for_sdf, target_for_colors, target_for_semantics,
                                                      view_matrix, intrinsics, transform)
+            locs, sdf_vals, color_vals, sem_vals = sparsify.sparsify_predictions(
+                output_sdf, T, empty, output_color, output_semantic, raycaster=self.raycaster, counted=counted)
+            output_normals = normals.compute_normals_sparse(locs, sdf_vals, self.dims3d, transform=transform)
             color = (color_vals + 1) * 0.5                                                     # train.py:623
             # prediction raycast + depth L1 + colour L1 + 2D semantic CE (train.py:626-643, 744-746), one kernel pair
             total2d, terms, _ = losses.render_with_2d_losses(

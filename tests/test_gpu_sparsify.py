@@ -90,3 +90,122 @@ def test_sparsify_predictions_feeds_the_raycaster(cuda_device):
     assert torch.equal(locs.cpu(), l)                                  # the generator's own (nonzero-ordered) voxel list
     assert torch.equal(vals_sdf.cpu(), torch.from_numpy(sdf_np))
     assert torch.equal(vals_sem, _literal_gather(dense_sem, locs))
+
+
+def _dense_heads(device, seeds):
+    """the synthetic chunks laid out as the generator's dense heads (SDF, colour, 14 logits)"""
+    from spsg_b200 import synthetic as S
+    batch = S.make_batch(seeds)
+    B = len(seeds)
+    dz, dy, dx = S.DIMS_ZYX
+    l = torch.from_numpy(batch["locs"])
+    idx = (l[:, 3], l[:, 0], l[:, 1], l[:, 2])
+    sdf = torch.full((B, dz, dy, dx), 2.0 * S.TRUNCATION)
+    sdf[idx] = torch.from_numpy(batch["sdf"][:, 0])
+    col = torch.zeros(B, dz, dy, dx, 3)
+    col[idx] = torch.from_numpy(batch["color"])
+    sem = torch.zeros(B, dz, dy, dx, 14)
+    sem[idx] = torch.from_numpy(batch["semantic"])
+    return (sdf.unsqueeze(1).contiguous().to(device), col.permute(0, 4, 1, 2, 3).contiguous().to(device),
+            sem.permute(0, 4, 1, 2, 3).contiguous().to(device))
+
+
+def _raycaster(B, F, device, n_max):
+    from spsg_b200 import synthetic as S
+    from spsg_b200.raycast_rgbd import RaycastRGBD
+    return RaycastRGBD(B, S.DIMS_ZYX, S.WIDTH, S.HEIGHT, S.DEPTH_MIN, S.DEPTH_MAX, S.THRESH_SAMPLE_DIST, S.RAY_INCREMENT,
+                       max_num_frames=F, max_num_locs_per_sample=n_max, device=device)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_direct_feed_equals_the_locs_round_trip(cuda_device, fused):
+    """sparsify_predictions(..., raycaster=m) writes m's voxel index and dense SDF brick in the pass that writes locs; the
+    forward over those rows then skips its fill + index passes (SPSG_FLAG_INDEX_PREBUILT).  Renderings, index, counters and
+    voxel gradients must equal, bit for bit, what the plain route (locs -> fill -> index) gives on a second module."""
+    from spsg_b200 import _native as N, losses, normals, sparsify, synthetic as S
+    from tests.common import views
+    B, F = 2, 2
+    sdf, col, sem = _dense_heads(cuda_device, [0, 1])
+    _, _, view, intr = views(B, F, cuda_device, seed=3)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    t_depth = (torch.rand(B * F, S.HEIGHT, S.WIDTH, generator=g) * 3.0).to(cuda_device)
+    t_color = torch.rand(B * F, S.HEIGHT, S.WIDTH, 3, generator=g).to(cuda_device)
+    t_label = torch.randint(0, 15, (B * F, S.HEIGHT, S.WIDTH), generator=g).to(torch.uint8).to(cuda_device)
+    out = []
+    for feed in (True, False):
+        m = _raycaster(B, F, cuda_device, 200000)
+        heads = [t.detach().clone().requires_grad_(True) for t in (sdf, col, sem)]
+        locs, v_sdf, v_col, v_sem = sparsify.sparsify_predictions(heads[0], S.TRUNCATION, None, heads[1], heads[2],
+                                                                  raycaster=m if feed else None)
+        assert (m.workspace._prebuilt is not None) == feed
+        if feed:
+            index_before = m.sparse_mapping.clone()
+        nrm = normals.compute_normals_sparse(locs, v_sdf.detach(), S.DIMS_ZYX, transform=torch.inverse(view[::F]), num_chunks=B)
+        if fused:
+            total, _, _ = losses.render_with_2d_losses(m, locs, v_sdf, v_col, nrm, v_sem, view, intr, images_depth=t_depth,
+                                                       images_color=t_color, target2d_label=t_label, voxelsize=S.VOXELSIZE)
+        else:
+            c, d, nn, s = m(locs, v_sdf, v_col, nrm, v_sem, view, intr)
+            hit = d != -float("inf")
+            total = d[hit].sum() * 0.01 + c[hit].sum() + s[hit].sum() * 0.1
+        if feed:
+            assert m.workspace._prebuilt is not None          # taken by the forward and still valid after it
+            assert torch.equal(index_before, m.sparse_mapping)  # the forward did not rebuild the index
+        total.backward()
+        out.append((locs, m.sparse_mapping.clone(), m.image_color.clone(), m.image_depth.clone(), m.image_normal.clone(),
+                    m.image_semantic.clone(), m.mapping3dto2d_num[:locs.shape[0] * F].clone(), total.detach().clone(),
+                    heads[0].grad.clone(), heads[1].grad.clone(), heads[2].grad.clone()))
+    names = ("locs", "sparse_mapping", "color", "depth", "normal", "semantic", "mapping3dto2d_num", "loss", "d_sdf", "d_color",
+             "d_semantic")
+    for a, b, name in zip(out[0], out[1], names):
+        if name.startswith("d_") or name == "loss":   # gradients: per-voxel means of atomically registered pixels
+            torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-6, msg=name)
+        else:
+            assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a,
+                               b.view(torch.int32) if b.dtype == torch.float32 else b), name
+    assert int((out[0][3] != -float("inf")).sum()) > 1000
+
+
+def test_direct_feed_mark_is_dropped_by_other_renders(cuda_device):
+    """The prebuilt index + brick belong to one locs tensor.  A render of other rows on the same module overwrites them:
+    the mark must be gone, and a later render of the first rows must rebuild (and still be right)."""
+    from spsg_b200 import sparsify, synthetic as S
+    from tests.common import scene_tensors, views
+    sdf, col, sem = _dense_heads(cuda_device, [0])
+    _, _, view, intr = views(1, 1, cuda_device, seed=5)
+    m = _raycaster(1, 1, cuda_device, 200000)
+    locs, v_sdf, v_col, v_sem = sparsify.sparsify_predictions(sdf, S.TRUNCATION, None, col, sem, raycaster=m)
+    nrm = torch.zeros(locs.shape[0], 3, device=cuda_device)
+    nrm[:, 2] = 1.0
+    with torch.no_grad():
+        first = [t.clone() for t in m(locs, v_sdf, v_col, nrm, v_sem, view, intr)]
+        assert m.workspace._prebuilt is not None
+        _, other = scene_tensors([7], cuda_device)
+        m(other["locs"], other["sdf"], other["color"], other["normal"], other["semantic"], view, intr)
+        assert m.workspace._prebuilt is None
+        again = m(locs, v_sdf, v_col, nrm, v_sem, view, intr)
+        for a, b in zip(first, again):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+        # a modified locs tensor no longer matches its mark either
+        locs2, v2, c2, s2 = sparsify.sparsify_predictions(sdf, S.TRUNCATION, None, col, sem, raycaster=m)
+        locs2[0, 0] += 0
+        assert m.workspace.take_prebuilt(locs2, 0) == 0
+
+
+def test_counted_locs_split(cuda_device):
+    """count_locs now, rows later (after other work): same rows; a count of other tensors is refused."""
+    from spsg_b200 import sparsify
+    sdf = _volume((2, 24, 16, 20), cuda_device, 11)
+    empty = _volume((2, 24, 16, 20), cuda_device, 12) > 1.0
+    counted = sparsify.count_locs(sdf, 2.5, empty)
+    other = sparsify.sparse_locs(_volume((2, 24, 16, 20), cuda_device, 13), 1.0)      # unrelated compaction in between
+    want = _literal_locs(sdf, 2.5, empty)
+    assert counted.n == want.shape[0] and other.shape[0] != counted.n
+    assert torch.equal(sparsify.sparse_locs(sdf, 2.5, empty, counted=counted), want)
+    with pytest.raises(RuntimeError):
+        sparsify.sparse_locs(sdf, 2.0, empty, counted=counted)                        # another truncation
+    with pytest.raises(RuntimeError):
+        sparsify.sparse_locs(sdf.clone(), 2.5, empty, counted=counted)                # another tensor
+    sdf[0, 0, 0, 0, 0] = 0.0
+    with pytest.raises(RuntimeError):
+        sparsify.sparse_locs(sdf, 2.5, empty, counted=counted)                        # modified since the count
