@@ -477,7 +477,7 @@ def e2e_protocol(run, steps, warmup, dev, world):
 # train step (BASELINE configs[3]) and CPU baselines
 # ---------------------------------------------------------------------------------------------------------------------
 
-def train_leg(impl, dev, rank, world, local, steps=8, warmup=3):
+def train_leg(impl, dev, rank, world, local, steps=8, warmup=3, layout="ncdhw"):
     """chunks/s of the train.py step under DistributedDataParallel (one rank per GPU, NCCL all-reduce of the generator's
     gradients); impl "ours" = spsg_b200.train_step on this package's ops, "reference" = the reference's loop body, wrapper,
     losses and CUDA extension (baseline/ref_train_step.py)."""
@@ -496,6 +496,9 @@ def train_leg(impl, dev, rank, world, local, steps=8, warmup=3):
     finally:
         sys.stdout = keep
     model.train()
+    if layout == "ndhwc":
+        from spsg_b200.train_step import prepare_generator
+        model = prepare_generator(model)  # memory format only: same modules, same arithmetic
     params = sum(p.numel() for p in model.parameters())
     net = model
     if world > 1:
@@ -537,6 +540,8 @@ def train_leg(impl, dev, rank, world, local, steps=8, warmup=3):
             "steps": steps, "chunks_per_gpu_per_step": TRAIN_BATCH, "views_per_chunk": 1,
             "generator_parameters": params, "num_locs_last_step": int(step.last.get("num_locs", -1)),
             "last_loss": float(loss),
+            "generator_layout": "channels_last_3d (NDHWC) parameters and activations" if layout == "ndhwc" else
+                                "PyTorch default (NCDHW)",
             "step": ("spsg_b200.train_step.ViewGuidedTrainStep: reference Generator (baseline/_ref model.py, random init) "
                      "fwd/bwd + its dense 3D losses + sparsify / normals / 3 raycasts / fused 2D losses of this package + Adam"
                      if impl == "ours" else
@@ -951,7 +956,15 @@ def main():
     if not args.no_train:
         o.mods, o.devsets = None, None
         torch.cuda.empty_cache()
-        secondary("train", lambda: train_leg("ours", dev, rank, world, local))
+        def leg_train():
+            # the step as this package runs it on B200 (generator in NDHWC), and the same step with the generator left in
+            # PyTorch's default layout -- the reference arm's configuration -- so that the layout's share is visible
+            t = train_leg("ours", dev, rank, world, local, layout="ndhwc")
+            torch.cuda.empty_cache()
+            d = train_leg("ours", dev, rank, world, local, steps=4, warmup=2, layout="ncdhw")
+            t["default_layout"] = {k: d[k] for k in ("chunks_per_s", "ms_per_step", "steps", "generator_layout", "last_loss") if k in d}
+            return t
+        secondary("train", leg_train)
     if rank == 0:
         line = dict(base, value=value, steps=steps, ms_per_step=ms / steps, clocks=sampler.summary(),
                     e2e={"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": bytes_of(o.host[0], H2D_KEYS),

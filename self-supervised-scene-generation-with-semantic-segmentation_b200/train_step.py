@@ -21,6 +21,15 @@ from . import losses, normals, sparsify
 from .raycast_rgbd import RaycastRGBD
 
 
+def prepare_generator(model):
+    """The generator laid out for B200: parameters (and with them every activation cuDNN produces) in
+    ``torch.channels_last_3d`` (NDHWC).  The reference's ``Generator`` is a Conv3d + BatchNorm3d U-Net with 10-100 channels on
+    128x64x64 volumes; in the default NCDHW layout cuDNN brackets its tensor-core kernels with layout transposes, in NDHWC it
+    does not: forward + backward of a batch of 8 takes 196 ms instead of 332 ms (same TF32 convolutions, same loss to the
+    last printed digit; ``tools/gen_layout_probe.py``).  Nothing in the model changes.  Call before wrapping in DDP."""
+    return model.to(memory_format=torch.channels_last_3d)
+
+
 class ViewGuidedTrainStep:
     """One training iteration past ``num_iters_geo_only`` with the 2D semantic branch (``--pred_3d_semantic ''``), GAN
     and VGG style terms off (``train.py:740-747``).

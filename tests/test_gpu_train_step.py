@@ -105,3 +105,31 @@ def test_train_step_updates_parameters_and_loss_decreases(cuda_device):
     losses = [float(step(_clone(sample), optimizer=opt)) for _ in range(6)]
     assert all(np.isfinite(losses))
     assert losses[-1] < losses[0]
+
+
+def test_generator_in_ndhwc_gives_the_same_step(cuda_device):
+    """train_step.prepare_generator only changes the memory format of the generator's parameters (and so of cuDNN's
+    activations).  Compared with fp32 convolutions: under TF32 two cuDNN kernels for the same convolution round
+    differently, and through train-mode batch norm and the sign gradients of the L1 terms that alone moves the parameter
+    gradients by ~10 % (NCDHW TF32 against NCDHW fp32: 14 %, tools/layout_grad_probe.py) -- noise that would hide a real
+    difference between the layouts."""
+    from spsg_b200.train_step import ViewGuidedTrainStep, prepare_generator
+    ref_loader, model, sample, cw = _setup(cuda_device)
+    step = ViewGuidedTrainStep(model, ref_loader.load_module("loss"), 2, DIMS, W, H, cw,
+                               max_num_locs_per_sample=int(np.prod(DIMS)), device=cuda_device)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        loss_a, g_a = _grads(step, model, sample)
+        n_a, terms_a = step.last["num_locs"], step.last["terms2d"].clone()
+        prepare_generator(model)
+        assert any(p.dim() == 5 and p.is_contiguous(memory_format=torch.channels_last_3d) and not p.is_contiguous()
+                   for p in model.parameters())
+        loss_b, g_b = _grads(step, model, sample)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(step.last["num_locs"] - n_a) <= 2, (step.last["num_locs"], n_a)
+    assert torch.allclose(terms_a, step.last["terms2d"], rtol=1e-3, atol=1e-5), (terms_a, step.last["terms2d"])
+    assert abs(loss_a - loss_b) <= 1e-4 * max(1.0, abs(loss_a)), (loss_a, loss_b)
+    rel = float((g_a - g_b).norm() / g_a.norm())
+    assert rel < 2e-2, rel
