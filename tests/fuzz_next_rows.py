@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from oracle import losses_ref as R
-from spsg_b200 import sparsify, losses as L
+from spsg_b200 import sparsify, losses as L, _native as N
 from spsg_b200.normals import compute_normals_sparse
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
@@ -36,6 +36,21 @@ for c in range(cases):
     locs = sparsify.sparse_locs(sdf, trunc, empty)
     if not torch.equal(locs, locs_ref):
         fail(c, "sparse_locs %s" % ((B, dz, dy, dx),)); continue
+    # the indexed variant (spsg_sparsify_locs_indexed): same rows, plus voxel index and SDF brick for every cell
+    counted = sparsify.count_locs(sdf, trunc, empty)
+    cells, n = sdf.numel(), counted.n
+    index = torch.full((cells,), 12345, dtype=torch.int32, device=dev)
+    brick = torch.zeros(cells, device=dev)
+    locs_i = torch.empty(n, 4, dtype=torch.int64, device=dev)
+    N.check(N.lib.spsg_sparsify_locs_indexed(N.ptr(counted.sdf), N.ptr(counted.empty), B, dz, dy, dx, trunc, N.ptr(counted.scratch),
+                                             N.ptr(locs_i), n, N.ptr(index), N.ptr(brick), torch.cuda.current_stream().cuda_stream))
+    want_index = torch.full((B, dz, dy, dx), -1, dtype=torch.int32, device=dev)
+    want_index[locs_ref[:, 3], locs_ref[:, 0], locs_ref[:, 1], locs_ref[:, 2]] = torch.arange(n, dtype=torch.int32, device=dev)
+    want_brick = torch.full((B, dz, dy, dx), -1, dtype=torch.int32, device=dev)  # 0xffffffff = absent
+    want_brick[mask] = sdf[:, 0][mask].view(torch.int32)
+    if not (torch.equal(locs_i, locs_ref) and torch.equal(index, want_index.view(-1)) and
+            torch.equal(brick.view(torch.int32), want_brick.view(-1))):
+        fail(c, "sparsify_locs_indexed %s" % ((B, dz, dy, dx),)); continue
     if locs.shape[0]:
         vals = sparsify.gather_dense(locs, *heads)
         vals = vals if isinstance(vals, tuple) else (vals,)
