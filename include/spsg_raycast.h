@@ -250,7 +250,9 @@ SPSG_API int spsg_depth_compute_normals(const float *camspace, float *normals, i
  *    reference and stop on the device as soon as a round leaves no hole, then camera space (may be NULL) + normals
  *    (depth_utils_cuda_kernel.cu:172-211) from the filled depth.  hole_counts: SPSG_DEPTH_MAX_FILL_ROUNDS + 1 device
  *    int32; [0] = holes of the input, [r] = holes left after round r (0 for rounds that did not run).  The caller reads
- *    hole_counts[max_fill_iters / 2] (one synchronisation) to decide whether the reference would have returned None. */
+ *    hole_counts[max_fill_iters / 2] (one synchronisation) to decide whether the reference would have returned None.
+ *    Two launches: the filter, then one cooperative grid-resident kernel for the fill rounds and the normals (devices without
+ *    cooperative launch, or the environment variable SPSG_DEPTH_NO_COOPERATIVE, get one launch per pass; same results). */
 SPSG_API int spsg_depth_to_normals(float *depth, const float *intrinsics, float *filtered, float *camspace, float *normals,
                                    int32_t *hole_counts, int32_t batch, int32_t height, int32_t width, float sigma_d,
                                    float sigma_r, int32_t max_fill_iters, void *stream);

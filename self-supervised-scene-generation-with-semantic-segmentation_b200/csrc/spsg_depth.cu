@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 
 #include "spsg_internal.h"
 #include "spsg_raycast.h"
@@ -348,13 +349,25 @@ int spsg_depth_to_normals(float *depth, const float *intrinsics, float *filtered
     {
         // fill rounds + normals: one cooperative launch when the device has them, with as many CTAs as are resident at
         // once or, if the tiles need several turns, the count that gives every CTA the same number of turns
-        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        static std::mutex mu;
+        static int cached_room[64] = {0};  // resident CTAs of the kernel per device; -1 = no cooperative launch
+        int dev = 0;
         SPSG_CUDA_TRY(cudaGetDevice(&dev));
-        SPSG_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        SPSG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        SPSG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_rounds_normals_kernel, 256, 0));
-        if (coop && per_sm > 0 && !getenv("SPSG_DEPTH_NO_COOPERATIVE")) {
-            const long long tiles = (long long)grid.x * grid.y * grid.z, room = (long long)sms * per_sm;
+        int resident = 0;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (dev < 0 || dev >= 64 || cached_room[dev] == 0) {
+                int coop = 0, per_sm = 0;
+                SPSG_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+                SPSG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_rounds_normals_kernel, 256, 0));
+                resident = (coop && per_sm > 0) ? spsg_internal_sm_count() * per_sm : -1;
+                if (dev >= 0 && dev < 64) cached_room[dev] = resident;
+            } else {
+                resident = cached_room[dev];
+            }
+        }
+        if (resident > 0 && !getenv("SPSG_DEPTH_NO_COOPERATIVE")) {
+            const long long tiles = (long long)grid.x * grid.y * grid.z, room = resident;
             const long long turns = (tiles + room - 1) / room;
             const int ctas = (int)((tiles + turns - 1) / turns);
             void *args[] = {&depth, &intrinsics, &filtered, &camspace, &normals, &hole_counts, &width, &height, &batch,
