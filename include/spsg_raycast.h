@@ -56,6 +56,8 @@ enum {
     SPSG_FLAG_GRADS_CLEARED = 1u << 3, /* backward only: rows [0,N) of d_* were cleared by the matching forward */
     SPSG_FLAG_SMEM_MAPS = 1u << 5,     /* debug: march maps staged in shared memory (TMA) even for several chunks          */
     SPSG_FLAG_GLOBAL_MAPS = 1u << 6,   /* debug: march maps read through L1 + one global tile counter even for one chunk   */
+    SPSG_FLAG_PACKED_LOCS = 1u << 8,   /* forward (entry points that build the index): `locs` points to num_locs uint32 linear
+                                          cell indices, the output of spsg_pack_locs_host, instead of int64 (z,y,x,b) rows      */
     SPSG_FLAG_INDEX_PREBUILT = 1u << 7, /* forward: sparse_mapping and the workspace's dense SDF brick already hold exactly
                                           these locs / vals_sdf (written by spsg_sparsify_locs_indexed): skip the -1 / NaN
                                           fill and the index pass (only mapping3dto2d_num is reset)                          */
@@ -223,6 +225,15 @@ SPSG_API int spsg_losses2d_backward(const spsg_loss_targets *t, const float *ima
                                     const float *image_semantic, int64_t num_pixels, const float *loss_out,
                                     const float *grad_scale, float *d_color, float *d_depth, float *d_semantic,
                                     void *stream);
+
+/* ---- host side of a host-fed call.  The reference hands its voxel rows to the GPU as int64 (z,y,x,b) -- 32 bytes per voxel, 28
+ *      of them zero -- (raycast_rgbd.py:22-28; data_util.py builds them from the chunk file's uint32 triples).  This packs them,
+ *      on the host, into what the index pass derives from them anyway: one uint32 linear cell index ((b*Dz+z)*Dy+y)*Dx+x per
+ *      row (0xffffffff for a row outside the grid, which the device skips like the int64 path does), to be written straight
+ *      into the pinned staging buffer and passed as `locs` with SPSG_FLAG_PACKED_LOCS: 4 instead of 32 bytes per voxel over
+ *      PCIe.  Plain host pointers, `threads` OpenMP threads (clamped to 1..64), no CUDA call.  Needs B*Dz*Dy*Dx < 2^32 - 1. */
+SPSG_API int spsg_pack_locs_host(const int64_t *locs, int64_t num_locs, int32_t num_chunks, int32_t dimz, int32_t dimy,
+                                 int32_t dimx, uint32_t *cells_out, int32_t threads);
 
 /* ---- depth-frame utilities: the reference's second extension on the training step, torch/utils/depth_utils
  *      (depth_utils_cuda.cpp:80-85, depth_utils_cuda_kernel.cu; Python depth_utils.py:46-100).  Images are (B,1,H,W)

@@ -18,6 +18,7 @@ SPSG_FLAG_DETERMINISTIC_GRADS = 1 << 4
 SPSG_FLAG_SMEM_MAPS = 1 << 5
 SPSG_FLAG_GLOBAL_MAPS = 1 << 6
 SPSG_FLAG_INDEX_PREBUILT = 1 << 7
+SPSG_FLAG_PACKED_LOCS = 1 << 8
 SPSG_LOSS_OUT_FLOATS = 8
 SPSG_DEPTH_MAX_FILL_ROUNDS = 64
 
@@ -31,7 +32,7 @@ EXPORTS = (
     "spsg_depth_compute_normals",
     "spsg_sparsify_scratch_bytes", "spsg_sparsify_count", "spsg_sparsify_locs", "spsg_sparsify_locs_indexed",
     "spsg_dense_gather", "spsg_dense_scatter",
-    "spsg_labels_from_render",
+    "spsg_labels_from_render", "spsg_pack_locs_host",
 )
 
 
@@ -127,6 +128,8 @@ def _load():
     lib.spsg_sparsify_count.argtypes = [vp, vp, i64, f32, vp, sz, vp, vp]
     lib.spsg_sparsify_locs.restype = ctypes.c_int
     lib.spsg_sparsify_locs.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, i64, vp]
+    lib.spsg_pack_locs_host.restype = ctypes.c_int
+    lib.spsg_pack_locs_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, i32]
     lib.spsg_sparsify_locs_indexed.restype = ctypes.c_int
     lib.spsg_sparsify_locs_indexed.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, vp, i64, vp, vp, vp]
     lib.spsg_dense_gather.restype = ctypes.c_int

@@ -37,6 +37,23 @@ __global__ void __launch_bounds__(256) fill_kernel(const FillArgs a) {
 
 // construct_dense_sparse_mapping_kernel (kernel.cu:346-362) + dense SDF scatter + voxel->pixel counter reset,
 // one pass over locs.
+// The same pass over rows that arrive as one uint32 linear cell index each (spsg_pack_locs_host: what this kernel derives
+// from the int64 row anyway; 0xffffffff = row outside the grid): 4 instead of 32 bytes per voxel read here -- and, before
+// that, carried over PCIe.
+__global__ void __launch_bounds__(256) index_packed_kernel(const uint32_t *__restrict__ cells, long long n,
+                                                           int32_t *__restrict__ sparse_mapping,
+                                                           const float *__restrict__ vals_sdf, float *__restrict__ dense,
+                                                           int32_t *__restrict__ num, int views, unsigned long long grid_cells) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (num)
+        for (int f = 0; f < views; f++) num[(long long)f * n + i] = 0;
+    const unsigned cell = __ldg(cells + i);
+    if ((unsigned long long)cell >= grid_cells) return;  // the sentinel, or an index outside this grid
+    sparse_mapping[cell] = (int32_t)i;
+    if (dense) dense[cell] = __ldg(vals_sdf + i);
+}
+
 template <bool kWriteIndex>
 __global__ void __launch_bounds__(256) index_kernel(const longlong4 *__restrict__ locs, long long n,
                                                     int32_t *__restrict__ sparse_mapping,

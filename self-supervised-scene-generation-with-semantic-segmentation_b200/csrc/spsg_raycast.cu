@@ -105,8 +105,12 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
         return fail(SPSG_ERR_INVALID_ARGUMENT, "NULL voxel tensor pointer");
     if (!aligned16(view_matrix) || !aligned16(intrinsics))
         return fail(SPSG_ERR_INVALID_ARGUMENT, "view_matrix / intrinsics must be 16-byte aligned");
-    if (p->num_locs > 0 && ((reinterpret_cast<uintptr_t>(vals_semantic) & 7u) || (reinterpret_cast<uintptr_t>(locs) & 15u)))
-        return fail(SPSG_ERR_INVALID_ARGUMENT, "vals_semantic must be 8-byte and locs 16-byte aligned");
+    const bool packed = (p->flags & SPSG_FLAG_PACKED_LOCS) != 0;
+    if (p->num_locs > 0 && ((reinterpret_cast<uintptr_t>(vals_semantic) & 7u) || (reinterpret_cast<uintptr_t>(locs) & (packed ? 3u : 15u))))
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "vals_semantic must be 8-byte and locs 16-byte (packed: 4-byte) aligned");
+    if (packed && !build_index) return fail(SPSG_ERR_INVALID_ARGUMENT, "packed locs need an entry point that builds the index");
+    if (packed && (unsigned long long)p->num_chunks * p->dimz * p->dimy * p->dimx >= 0xffffffffull)
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "packed locs need fewer than 2^32 - 1 cells");
     if (reinterpret_cast<uintptr_t>(sparse_mapping) & 3u) return fail(SPSG_ERR_INVALID_ARGUMENT, "sparse_mapping must be 4-byte aligned");
     if (targets && !loss_out) return fail(SPSG_ERR_INVALID_ARGUMENT, "loss_out is NULL");
     const Layout L = make_layout(p);
@@ -145,7 +149,10 @@ int launch_forward(const spsg_raycast_params *p, bool build_index, int32_t *spar
     }
     if (p->num_locs > 0 && !prebuilt) {
         const unsigned blocks = (unsigned)((p->num_locs + 255) / 256);
-        if (build_index)
+        if (packed)
+            index_packed_kernel<<<blocks, 256, 0, st>>>((const uint32_t *)locs, p->num_locs, sparse_mapping, vals_sdf, dense,
+                                                        mapping3dto2d_num, p->views_per_chunk, (unsigned long long)cells);
+        else if (build_index)
             index_kernel<true><<<blocks, 256, 0, st>>>((const longlong4 *)locs, p->num_locs, sparse_mapping, vals_sdf,
                                                        dense, mapping3dto2d_num, p->views_per_chunk, p->dimz, p->dimy,
                                                        p->dimx, p->num_chunks);
@@ -570,3 +577,22 @@ int spsg_losses2d_backward(const spsg_loss_targets *t, const float *image_color,
 }
 
 }  // extern "C"
+
+// ---- host side of a host-fed call (no CUDA in here)
+extern "C" SPSG_API int spsg_pack_locs_host(const int64_t *locs, int64_t num_locs, int32_t num_chunks, int32_t dimz,
+                                            int32_t dimy, int32_t dimx, uint32_t *cells_out, int32_t threads) {
+    if (num_locs < 0 || (num_locs > 0 && (!locs || !cells_out))) return fail(SPSG_ERR_INVALID_ARGUMENT, "bad locs / output");
+    if (num_chunks <= 0 || dimz <= 0 || dimy <= 0 || dimx <= 0) return fail(SPSG_ERR_INVALID_ARGUMENT, "bad grid sizes");
+    if ((unsigned long long)num_chunks * dimz * dimy * dimx >= 0xffffffffull)
+        return fail(SPSG_ERR_INVALID_ARGUMENT, "packed locs need fewer than 2^32 - 1 cells");
+    const int t = std::max(1, std::min(threads, 64));
+    const long long dz = dimz, dy = dimy, dx = dimx, nb = num_chunks;
+#pragma omp parallel for num_threads(t) schedule(static)
+    for (long long i = 0; i < (long long)num_locs; i++) {
+        const long long z = locs[4 * i], y = locs[4 * i + 1], x = locs[4 * i + 2], b = locs[4 * i + 3];
+        const bool in = (unsigned long long)z < (unsigned long long)dz && (unsigned long long)y < (unsigned long long)dy &&
+                        (unsigned long long)x < (unsigned long long)dx && (unsigned long long)b < (unsigned long long)nb;
+        cells_out[i] = in ? (uint32_t)(((b * dz + z) * dy + y) * dx + x) : 0xffffffffu;
+    }
+    return SPSG_OK;
+}

@@ -85,6 +85,8 @@ def fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, v
         raise RuntimeError("raycaster buffers live on %s, inputs on %s" % (m.image_depth.device, dev))
     p = N.make_params(m.width, m.height, m.depth_min, m.depth_max, m.thresh_sample_dist, m.ray_increment,
                       m.dims3d[2], m.dims3d[1], m.dims3d[0], m.batch_size, views, m.mapping3dto2d.shape[1], n, m.flags)
+    if rc.is_packed_locs(locs):
+        p.flags |= N.SPSG_FLAG_PACKED_LOCS
     target_depth, target_color, weight_color, target_label, class_weight, voxelsize, weights = targets
     tg = _targets_struct(images, m.height, m.width, target_depth, target_color, weight_color, target_label, class_weight,
                          voxelsize, weights)
@@ -107,6 +109,7 @@ def fused_forward(m, locs, vals_sdf, vals_colors, vals_normals, vals_semantic, v
         if prebuilt:
             owner.mark_prebuilt(locs)
             p.flags &= ~N.SPSG_FLAG_INDEX_PREBUILT  # (the params go on to the backward)
+        p.flags &= ~N.SPSG_FLAG_PACKED_LOCS
     return p, tg, loss_out
 
 

@@ -15,6 +15,7 @@ Same four entry points, positional tensors, in-place outputs and error behaviour
 import ctypes
 from collections import OrderedDict
 
+import os
 import weakref
 
 import torch
@@ -51,12 +52,13 @@ def check_voxel_inputs(locs, vals_sdf, vals_color, vals_normals, vals_semantic, 
     for t, name in ((locs, "locs"), (vals_sdf, "vals_sdf"), (vals_color, "vals_color"), (vals_normals, "vals_normals"),
                     (vals_semantic, "vals_semantic"), (view_matrix, "viewMatrixInv"), (intrinsic_params, "intrinsicParams")):
         _check_input(t, name)
-    _check_dtype(locs, torch.int64, "locs")
+    if not is_packed_locs(locs):
+        _check_dtype(locs, torch.int64, "locs")
     for t, name in ((vals_sdf, "vals_sdf"), (vals_color, "vals_color"), (vals_normals, "vals_normals"),
                     (vals_semantic, "vals_semantic"), (view_matrix, "viewMatrixInv"), (intrinsic_params, "intrinsicParams")):
         _check_dtype(t, torch.float32, name)
     n = locs.shape[0]
-    if locs.numel() != 4 * n:
+    if not is_packed_locs(locs) and locs.numel() != 4 * n:
         raise RuntimeError("locs must be (N, 4) rows of (z, y, x, chunk)")
     if vals_sdf.numel() < n or vals_color.numel() < 3 * n or vals_normals.numel() < 3 * n or vals_semantic.numel() < 14 * n:
         raise RuntimeError("voxel value tensors hold fewer than N = %d rows" % n)
@@ -66,6 +68,31 @@ def check_voxel_inputs(locs, vals_sdf, vals_color, vals_normals, vals_semantic, 
     if len(devs) != 1:
         raise RuntimeError("raycast inputs live on different devices: %s" % sorted(str(d) for d in devs))
     return n
+
+
+def is_packed_locs(locs):
+    """``locs`` given as one linear cell index per voxel, (N,) int32 holding uint32 bits -- the output of ``pack_locs_host``
+    after its trip over PCIe -- instead of the reference's (N,4) int64 rows."""
+    return locs.dim() == 1 and locs.dtype == torch.int32
+
+
+def pack_locs_host(locs, num_chunks, dims3d, out=None, threads=0):
+    """Host side of a host-fed call: the reference's (N,4) int64 (z,y,x,b) rows, in host memory, as one uint32 linear cell
+    index each (``spsg_pack_locs_host``): 4 instead of 32 bytes per voxel to carry over PCIe.  ``out``: (N,) int32 CPU tensor to
+    write (e.g. a view of the pinned staging buffer); returned.  Pass its device copy as ``locs`` to the forward.
+    ``threads`` 0 = the CPUs this process may run on (at most 16)."""
+    if locs.device.type != "cpu" or locs.dtype != torch.int64 or not locs.is_contiguous() or locs.dim() != 2 or locs.shape[1] != 4:
+        raise RuntimeError("pack_locs_host takes a contiguous (N,4) int64 CPU tensor")
+    n = locs.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32)
+    if out.device.type != "cpu" or out.dtype != torch.int32 or not out.is_contiguous() or out.numel() != n:
+        raise RuntimeError("out must be a contiguous (N,) int32 CPU tensor")
+    if threads <= 0:
+        threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    N.check(N.lib.spsg_pack_locs_host(locs.data_ptr(), n, int(num_chunks), int(dims3d[0]), int(dims3d[1]), int(dims3d[2]),
+                                      out.data_ptr(), int(threads)))
+    return out
 
 
 def _stamp(p):
@@ -199,6 +226,10 @@ def forward(sparse_mapping, locs, vals_sdf, vals_color, vals_normals, vals_seman
                     (imageSemantic, "imageSemantic")):
         _check_dtype(t, torch.float32, name)
     p = _forward_params(sparse_mapping, locs, mapping3dto2d, opts, views_per_chunk, flags)
+    if is_packed_locs(locs):
+        if not build_index:
+            raise RuntimeError("packed locs need build_index=True")
+        p.flags |= N.SPSG_FLAG_PACKED_LOCS
     images = p.num_chunks * p.views_per_chunk
     n = check_voxel_inputs(locs, vals_sdf, vals_color, vals_normals, vals_semantic, viewMatrixInv, intrinsicParams, images)
     if mapping3dto2d_num.numel() < p.views_per_chunk * n or mapping3dto2d.shape[0] < p.views_per_chunk * n:
