@@ -81,3 +81,14 @@ def test_patch_reference_loss_module():
     assert fake.compute_2dcolor_loss is losses.color_l1_loss
     assert list(inspect.signature(normals.compute_normals_sparse).parameters)[:4] == ["sdf_locs", "sdf_vals", "dims", "transform"]
     assert list(inspect.signature(losses.color_l1_loss).parameters) == ["raycast_color", "target_color", "weight_color"]
+
+
+def test_flag_constants_match_the_header():
+    """every SPSG_FLAG_* of include/spsg_raycast.h has the same value in the ctypes mirror, and no two flags share a bit"""
+    from spsg_b200 import _native as N
+    text = open(os.path.join(ROOT, "include", "spsg_raycast.h")).read()
+    flags = {name: int(shift) for name, shift in re.findall(r"\b(SPSG_FLAG_\w+)\s*=\s*1u\s*<<\s*(\d+)", text)}
+    assert len(flags) >= 8
+    assert len(set(flags.values())) == len(flags)
+    for name, shift in flags.items():
+        assert getattr(N, name) == 1 << shift, name
