@@ -33,3 +33,9 @@ def test_fuzz_backward_slice(cuda_device):
 def test_fuzz_fused_losses_slice(cuda_device):
     from tests import fuzz_fused
     assert fuzz_fused.run(cases=60, seed0=47, dev=cuda_device) == 0
+
+
+def test_fuzz_alternative_routes_slice(cuda_device):
+    """host-packed rows and the index + brick written by the compaction pass against the plain int64 route"""
+    from tests import fuzz_routes
+    assert fuzz_routes.run(cases=120, seed0=5, dev=cuda_device) == 0
